@@ -1,0 +1,139 @@
+/* irr_b200 — C ABI of the B200-native IRR-PWC inference hot path (sm_100a).
+ *
+ * This is the drop-in boundary.  It replaces
+ *   (1) the reference's pybind11 extension `correlation_cuda`
+ *         int forward(Tensor& input1, Tensor& input2, Tensor& rInput1, Tensor& rInput2, Tensor& output,
+ *                     int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+ *                     int corr_type_multiply)            — models/correlation_package/correlation_cuda.cc:8-14,165-168
+ *   (2) the ATen library ops the PWC models actually execute on the path (conv2d+leaky_relu, grid_sampler_2d,
+ *       upsample_bilinear2d, the 81-iteration slice/mul/mean loop of compute_cost_volume, softmax/unfold of
+ *       RefineFlow/RefineOcc) — call sites cited per function below.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no C++/torch types.  `irr_stream_t` is a cudaStream_t/CUstream.
+ *   - every tensor is fp32, NCHW, W-contiguous; a tensor argument is (pointer, batch_stride) where the pointer
+ *     already points at the first channel of a channel-slice of a possibly larger buffer and `*_bs` is the
+ *     distance in ELEMENTS between consecutive batch items (= C_total*H*W of the owning buffer).  This is how the
+ *     reference's torch.cat() concatenations are eliminated: producers write straight into channel slices.
+ *   - device = the caller's current CUDA device; pointers are device pointers owned by the caller (PyTorch's
+ *     caching allocator).  The library never allocates, frees or synchronises; launches are asynchronous on
+ *     `stream`, so calls are capturable into CUDA graphs.
+ *   - return 0 on success; <0 = argument error (IRR_E_*), >0 = cudaError_t from the launch.  Never throws.
+ *     `irr_last_error()` returns a thread-local message.  (The reference printf()s and returns 0/1, turned into
+ *     AT_ERROR -> RuntimeError by correlation_cuda.cc:78-80; the Python host in irr_b200/_lib.py raises
+ *     RuntimeError on any non-zero return to keep that behaviour.)
+ *   - re-entrant per stream; no global mutable state except the error string and one-time function attributes.
+ */
+#ifndef IRR_B200_H_
+#define IRR_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* irr_stream_t;
+
+#define IRR_ABI_VERSION 1
+
+#define IRR_E_ARG (-1)       /* null pointer / non-positive size / unsupported parameter */
+#define IRR_E_ALIGN (-2)     /* pointer alignment requirement violated */
+#define IRR_E_UNSUPPORTED (-3)
+
+/* grid flags for the warp family */
+#define IRR_GRID_TRUE_DIV 0   /* flow*2/(dim-1)/div_flow with IEEE divisions: what the reference computes on the CPU */
+#define IRR_GRID_RECIP_MUL 1  /* a*(1/b): what torch's CUDA `tensor / python_scalar` computes */
+
+/* conv math modes */
+#define IRR_MATH_FP32_SIMT 0  /* CUDA-core FFMA implicit GEMM, fp32 accumulate */
+#define IRR_MATH_TC_3XTF32 1  /* tcgen05 kind::tf32, hi/lo split (3 MMAs) — fp32-grade accuracy */
+#define IRR_MATH_TC_TF32 2    /* tcgen05 kind::tf32 single pass — ~1e-3 relative, opt-in */
+
+int irr_abi_version(void);
+const char* irr_last_error(void);
+/* sm count / compute capability of the current device. */
+int irr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* A1 + A3 — cost volume of models/pwc_modules.py:42-62 (== Correlation(pad=md, k=1, md, 1, 1) of
+ * correlation_package/correlation.py:47-61 -> correlation_cuda_kernel.cu:41-114):
+ *   out[b, (dy+md)*(2md+1)+(dx+md), y, x] = act( (1/C) * sum_c f1[b,c,y,x] * f2[b2,c,y+dy,x+dx] ),  zero outside,
+ *   b2 = (b + f2_batch_shift) mod B,  act(v) = v>0 ? v : leaky_slope*v  (IRR_PWC.py:94-95; pass 1.0f for none).
+ * Only max_disp == 4 is compiled (the only value any PWC model uses, IRR_PWC.py:19). */
+int irr_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long long f2_bs, float* out,
+                        long long out_bs, int B, int C, int H, int W, int max_disp, int f2_batch_shift,
+                        float leaky_slope, irr_stream_t stream);
+
+/* A2 fused into A1 — out = act(cost_volume(f1, mask*warp(f2, flow))) without materialising the warped tensor
+ * (IRR_PWC.py:86-95).  warp = WarpingLayer.forward of models/pwc_modules.py:119-133: bilinear grid_sample
+ * (align_corners=True, zeros padding) at  lin_x[x] + flow_u*2/max(W_im-1,1)/div_flow  (likewise y), times the hard
+ * mask (sum of in-bounds bilinear weights >= 1.0f), with PyTorch's grid_sampler_2d weight arithmetic reproduced
+ * op for op so the mask is bit-identical.  lin_x (W floats) / lin_y (H floats) are the host torch.linspace(-1,1,n)
+ * vectors the reference uploads (pwc_modules.py:108-111); NULL => computed in-kernel as -1 + i*(2/(n-1)).
+ * flow is B x 2 x H x W (channel 0 = u). */
+int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,
+                             long long flow_bs, const float* lin_x, const float* lin_y, float* out, long long out_bs,
+                             int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
+                             int f2_batch_shift, float leaky_slope, int grid_flags, irr_stream_t stream);
+
+/* A2 standalone — out[b] = mask*warp(x[(b+x_batch_shift) mod B], flow[b]);  if minuend != NULL:
+ * out = minuend - mask*warp(...)   (IRR_PWC.py:132-133,144-145 feed `a - warp(b)` to the refinement nets).
+ * mask_out (optional, B x H x W floats 0/1) receives the validity mask. */
+int irr_warp_fwd(const float* x, long long x_bs, const float* flow, long long flow_bs, const float* lin_x,
+                 const float* lin_y, const float* minuend, long long minuend_bs, float* out, long long out_bs,
+                 float* mask_out, int B, int C, int H, int W, int H_im, int W_im, float div_flow, int x_batch_shift,
+                 int grid_flags, irr_stream_t stream);
+
+/* Generic Correlation (kernel_size odd >= 1, stride1, stride2, pad_size) for API completeness of
+ * correlation_package/correlation.py:47-61; output shape per correlation_cuda.cc:23-32.  corr_type_multiply is
+ * ignored exactly like the reference.  Simple kernel, not tuned (no PWC model uses k>1 or strides>1). */
+int irr_correlation_generic_fwd(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                                int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                                irr_stream_t stream);
+int irr_correlation_generic_out_shape(int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,
+                                      int stride2, int* out_c, int* out_h, int* out_w);
+
+/* A4-A7, A9, A10 — conv() of models/pwc_modules.py:8-19 (Conv2d k in {1,3}, padding=((k-1)*dilation)//2, bias,
+ * optional LeakyReLU) as an implicit GEMM, with the reference's torch.cat / residual adds folded in:
+ *   y = addend + alpha * act(conv(x, w) + bias)      (addend may be NULL; alpha = 1 for the plain case)
+ * x: B x Cin x H x W slice, y: B x Cout x Ho x Wo slice, Ho = floor((H + 2*pad - dil*(k-1) - 1)/stride) + 1.
+ * w_packed: produced by irr_conv2d_pack_weights for the same `math`. */
+size_t irr_conv2d_packed_bytes(int Cout, int Cin, int ksize, int math);
+int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int Cin, int ksize, int math,
+                            irr_stream_t stream);
+int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
+                   long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
+                   int stride, int dilation, float leaky_slope, float alpha, int math, irr_stream_t stream);
+
+/* A8 — upsample2d_as (models/pwc_modules.py:65-67): bilinear, align_corners=True, any in/out size, fused with an
+ * optional per-channel-parity scale (even channels * scale_even, odd * scale_odd): rescale_flow of
+ * pwc_modules.py:70-82 applied to the resized flow, or the final *(1/div_flow) of IRR_PWC.py:176. */
+int irr_resize_bilinear_ac_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
+                               int OH, int OW, float scale_even, float scale_odd, irr_stream_t stream);
+
+/* A8 — rescale_flow value semantics / channel-slice copy: y[b,c] = x[b,c] * (c even ? scale_even : scale_odd). */
+int irr_scale_channels_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
+                           float scale_even, float scale_odd, irr_stream_t stream);
+
+/* A10 — upsample_factor2 (models/irr_modules.py:21-27): nearest x2, then (only if (OH,OW) != (2H,2W)) bilinear
+ * align_corners=False resize to OH x OW. */
+int irr_upsample_nearest2x_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
+                               int OH, int OW, irr_stream_t stream);
+
+/* A9 head — RefineFlow input preparation (models/irr_modules.py:59-60,85-88):
+ *   y[b,c] = x[b,c] - mean_w(mean_h(x[b,c]))  for C channels.  One CTA per (b,c). */
+int irr_sub_spatial_mean_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
+                             irr_stream_t stream);
+/*   y[b,0] = sqrt(sum_c x[b,c]^2)   (torch.norm(p=2, dim=1), irr_modules.py:86). */
+int irr_channel_l2norm_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
+                           irr_stream_t stream);
+
+/* A9 tail — softmax(-logits^2) over the 9 taps, applied to the replicate-padded 3x3 neighbourhood of every
+ * channel of src (models/irr_modules.py:89-104, 130-138).  logits: B x 9 x H x W, src/out: B x C x H x W. */
+int irr_refine_gather_fwd(const float* logits, long long logits_bs, const float* src, long long src_bs, float* out,
+                          long long out_bs, int B, int C, int H, int W, irr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRR_B200_H_ */

@@ -1,0 +1,71 @@
+// Error plumbing and device queries for the irr_b200 C ABI (include/irr_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace irr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail_arg(const char* fn, const char* what) {
+  set_error("%s: invalid argument: %s", fn, what);
+  return IRR_E_ARG;
+}
+
+// The reference launcher checks cudaGetLastError() after its launches and reports failure
+// (correlation_cuda_kernel.cu:383-392); same contract, but the code is returned instead of printf'd.
+int check_launch(const char* fn) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA launch failed: %s", fn, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace irr
+
+extern "C" {
+
+int irr_abi_version(void) { return IRR_ABI_VERSION; }
+
+const char* irr_last_error(void) { return irr::g_err; }
+
+int irr_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    irr::set_error("irr_device_info: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  int n = 0, ma = 0, mi = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev);
+  if (sm_count) *sm_count = n;
+  if (cc_major) *cc_major = ma;
+  if (cc_minor) *cc_minor = mi;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// C-ABI dispatch for conv() (include/irr_b200.h): routes to the CUDA-core path (conv_simt.cu) or the tcgen05 path
+// (conv_tc.cu) according to `math`.  There is no CPU or library fallback: an unsupported request is an error.
+#include "common.cuh"
+
+namespace irr {
+size_t simt_packed_bytes(int Cout, int Cin, int ks);
+int simt_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st);
+int simt_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
+              float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil,
+              float slope, float alpha, cudaStream_t st);
+size_t tc_packed_bytes(int Cout, int Cin, int ks, int math);
+int tc_pack(const float* w, void* out, int Cout, int Cin, int ks, int math, cudaStream_t st);
+int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
+            float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
+            float alpha, int math, cudaStream_t st);
+bool tc_supported(int Cout, int Cin, int ks, int stride, int dil);
+}  // namespace irr
+
+using namespace irr;
+
+extern "C" {
+
+size_t irr_conv2d_packed_bytes(int Cout, int Cin, int ksize, int math) {
+  if (Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3)) return 0;
+  if (math == IRR_MATH_FP32_SIMT) return simt_packed_bytes(Cout, Cin, ksize);
+  if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32) return tc_packed_bytes(Cout, Cin, ksize, math);
+  return 0;
+}
+
+int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int Cin, int ksize, int math,
+                            irr_stream_t stream) {
+  const char* fn = "irr_conv2d_pack_weights";
+  IRR_REQUIRE(w_oihw && w_packed, fn, "null pointer");
+  IRR_REQUIRE(Cout > 0 && Cin > 0, fn, "non-positive size");
+  IRR_REQUIRE(ksize == 1 || ksize == 3, fn, "kernel_size must be 1 or 3");
+  IRR_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, fn, "w_packed must be 16-byte aligned");
+  if (math == IRR_MATH_FP32_SIMT) return simt_pack(w_oihw, w_packed, Cout, Cin, ksize, as_stream(stream));
+  if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32)
+    return tc_pack(w_oihw, w_packed, Cout, Cin, ksize, math, as_stream(stream));
+  return fail_arg(fn, "unknown math mode");
+}
+
+int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
+                   long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
+                   int stride, int dilation, float leaky_slope, float alpha, int math, irr_stream_t stream) {
+  const char* fn = "irr_conv2d_fwd";
+  IRR_REQUIRE(x && w_packed && bias && y, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
+  IRR_REQUIRE(ksize == 1 || ksize == 3, fn, "kernel_size must be 1 or 3");
+  IRR_REQUIRE(stride >= 1 && dilation >= 1, fn, "stride/dilation must be >= 1");
+  IRR_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, fn, "w_packed must be 16-byte aligned");
+  if (math == IRR_MATH_FP32_SIMT)
+    return simt_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
+                     leaky_slope, alpha, as_stream(stream));
+  if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32) {
+    if (!tc_supported(Cout, Cin, ksize, stride, dilation)) {
+      set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);
+      return IRR_E_UNSUPPORTED;
+    }
+    return tc_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
+                   leaky_slope, alpha, math, as_stream(stream));
+  }
+  return fail_arg(fn, "unknown math mode");
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI (include/irr_b200.h).
+
+Every function takes fp32 CUDA tensors that are NCHW channel-slices (``buf[:, a:b]`` of a contiguous buffer is
+fine: stride(1)=H*W, stride(2)=W, stride(3)=1) and launches on torch's current stream.  ``out=`` lets callers write
+straight into a channel slice of a pre-allocated concat buffer — that is how every torch.cat of the reference
+disappears.  No function here has a non-CUDA path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+MATH_FP32_SIMT = 0
+MATH_TC_3XTF32 = 1
+MATH_TC_TF32 = 2
+
+GRID_TRUE_DIV = 0   # reference-on-CPU arithmetic (IEEE divisions)
+GRID_RECIP_MUL = 1  # torch-CUDA `tensor / python_scalar` arithmetic (a * (1/b))
+
+_grid_mode = GRID_TRUE_DIV
+
+
+def set_grid_mode(mode: int) -> None:
+    """Select which reference arithmetic the warp grid reproduces bit-for-bit (see include/irr_b200.h)."""
+    global _grid_mode
+    assert mode in (GRID_TRUE_DIV, GRID_RECIP_MUL)
+    _grid_mode = mode
+
+
+def get_grid_mode() -> int:
+    return _grid_mode
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _v(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int]:
+    """(data_ptr, batch_stride_in_elements) of an NCHW channel-slice view."""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
+        raise RuntimeError(f"irr_b200: {name} must be a 4-D fp32 CUDA tensor (got {t.dtype}, {t.device}, dim {t.dim()})")
+    B, Cc, H, W = t.shape
+    s = t.stride()
+    ok = (W == 1 or s[3] == 1) and (H == 1 or s[2] == W) and (Cc == 1 or s[1] == H * W)
+    if not ok:
+        raise RuntimeError(f"irr_b200: {name} is not an NCHW channel-slice view (shape {tuple(t.shape)}, strides {s})")
+    bs = s[0] if B > 1 else Cc * H * W
+    return t.data_ptr(), bs
+
+
+_lin_cache = {}
+
+
+def host_linspace(n: int, device) -> torch.Tensor:
+    """The base-grid vector exactly as the reference makes it: CPU torch.linspace(-1, 1, n), uploaded
+    (models/pwc_modules.py:108-111) — cached per (n, device) instead of rebuilt on every call."""
+    key = (n, str(device))
+    t = _lin_cache.get(key)
+    if t is None:
+        t = torch.linspace(-1.0, 1.0, n).to(device)
+        _lin_cache[key] = t
+    return t
+
+
+def _new(like: torch.Tensor, C: int, H: int, W: int) -> torch.Tensor:
+    return torch.empty((like.shape[0], C, H, W), dtype=torch.float32, device=like.device)
+
+
+def correlation(f1, f2, out=None, shift: int = 0, slope: float = 1.0, max_disp: int = 4):
+    B, C, H, W = f1.shape
+    assert f2.shape == f1.shape
+    D = (2 * max_disp + 1) ** 2
+    if out is None:
+        out = _new(f1, D, H, W)
+    assert out.shape == (B, D, H, W)
+    p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); po, so = _v(out, "out")
+    rc = _lib.load().irr_correlation_fwd(p1, s1, p2, s2, po, so, B, C, H, W, max_disp, shift, slope, _stream())
+    _lib.check(rc, "correlation")
+    return out
+
+
+def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: float, out=None, shift: int = 0,
+                     slope: float = 1.0, max_disp: int = 4, lin_x=None, lin_y=None):
+    B, C, H, W = f1.shape
+    assert f2.shape == f1.shape and flow.shape == (B, 2, H, W)
+    D = (2 * max_disp + 1) ** 2
+    if out is None:
+        out = _new(f1, D, H, W)
+    lx = host_linspace(W, f1.device) if lin_x is None else lin_x
+    ly = host_linspace(H, f1.device) if lin_y is None else lin_y
+    p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
+    rc = _lib.load().irr_warp_correlation_fwd(p1, s1, p2, s2, pf, sf, lx.data_ptr(), ly.data_ptr(), po, so, B, C, H, W,
+                                              height_im, width_im, div_flow, max_disp, shift, slope, _grid_mode,
+                                              _stream())
+    _lib.check(rc, "warp_correlation")
+    return out
+
+
+def warp(x, flow, height_im: int, width_im: int, div_flow: float, out=None, minuend=None, shift: int = 0,
+         mask_out=None, lin_x=None, lin_y=None):
+    B, C, H, W = x.shape
+    assert flow.shape == (B, 2, H, W)
+    if out is None:
+        out = _new(x, C, H, W)
+    lx = host_linspace(W, x.device) if lin_x is None else lin_x
+    ly = host_linspace(H, x.device) if lin_y is None else lin_y
+    px, sx = _v(x, "x"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
+    pm, sm = (_v(minuend, "minuend") if minuend is not None else (None, 0))
+    rc = _lib.load().irr_warp_fwd(px, sx, pf, sf, lx.data_ptr(), ly.data_ptr(), pm, sm, po, so,
+                                  mask_out.data_ptr() if mask_out is not None else None, B, C, H, W, height_im,
+                                  width_im, div_flow, shift, _grid_mode, _stream())
+    _lib.check(rc, "warp")
+    return out
+
+
+def correlation_generic(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
+    import ctypes
+    B, C, H, W = in1.shape
+    in1 = in1.contiguous(); in2 = in2.contiguous()
+    oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib = _lib.load()
+    _lib.check(lib.irr_correlation_generic_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                                                     ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)),
+               "correlation_generic_out_shape")
+    out = torch.empty((B, oc.value, oh.value, ow.value), dtype=torch.float32, device=in1.device)
+    _lib.check(lib.irr_correlation_generic_fwd(in1.data_ptr(), in2.data_ptr(), out.data_ptr(), B, C, H, W, pad_size,
+                                               kernel_size, max_displacement, stride1, stride2, _stream()),
+               "correlation_generic")
+    return out
+
+
+def conv_out_hw(H: int, W: int, ks: int, stride: int, dil: int) -> Tuple[int, int]:
+    pad = ((ks - 1) * dil) // 2
+    return (H + 2 * pad - dil * (ks - 1) - 1) // stride + 1, (W + 2 * pad - dil * (ks - 1) - 1) // stride + 1
+
+
+def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
+    Cout, Cin, ks, ks2 = w.shape
+    assert ks == ks2
+    lib = _lib.load()
+    n = lib.irr_conv2d_packed_bytes(Cout, Cin, ks, math)
+    if n == 0:
+        raise RuntimeError(f"irr_b200: no packed layout for conv {Cout}x{Cin}x{ks} math={math}")
+    packed = torch.empty(n // 4, dtype=torch.float32, device=w.device)
+    wc = w.detach().contiguous().float()
+    _lib.check(lib.irr_conv2d_pack_weights(wc.data_ptr(), packed.data_ptr(), Cout, Cin, ks, math, _stream()),
+               "conv2d_pack_weights")
+    return packed
+
+
+def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, slope: float = 0.1, out=None,
+           addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT):
+    B, Cin, H, W = x.shape
+    Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
+    if out is None:
+        out = _new(x, Cout, Ho, Wo)
+    assert out.shape == (B, Cout, Ho, Wo), (out.shape, (B, Cout, Ho, Wo))
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    pa, sa = (_v(addend, "addend") if addend is not None else (None, 0))
+    if addend is not None:
+        assert addend.shape == out.shape
+    rc = _lib.load().irr_conv2d_fwd(px, sx, packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks,
+                                    stride, dil, slope, alpha, math, _stream())
+    _lib.check(rc, "conv2d")
+    return out
+
+
+def resize_ac(x, OH: int, OW: int, out=None, s_even: float = 1.0, s_odd: float = 1.0):
+    B, C, H, W = x.shape
+    if out is None:
+        out = _new(x, C, OH, OW)
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    _lib.check(_lib.load().irr_resize_bilinear_ac_fwd(px, sx, po, so, B, C, H, W, OH, OW, s_even, s_odd, _stream()),
+               "resize_bilinear_ac")
+    return out
+
+
+def scale_channels(x, out=None, s_even: float = 1.0, s_odd: float = 1.0):
+    B, C, H, W = x.shape
+    if out is None:
+        out = _new(x, C, H, W)
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    _lib.check(_lib.load().irr_scale_channels_fwd(px, sx, po, so, B, C, H * W, s_even, s_odd, _stream()),
+               "scale_channels")
+    return out
+
+
+def upsample_nearest2x(x, OH: int, OW: int, out=None):
+    B, C, H, W = x.shape
+    if out is None:
+        out = _new(x, C, OH, OW)
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    _lib.check(_lib.load().irr_upsample_nearest2x_fwd(px, sx, po, so, B, C, H, W, OH, OW, _stream()),
+               "upsample_nearest2x")
+    return out
+
+
+def sub_spatial_mean(x, out=None):
+    B, C, H, W = x.shape
+    if out is None:
+        out = _new(x, C, H, W)
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    _lib.check(_lib.load().irr_sub_spatial_mean_fwd(px, sx, po, so, B, C, H, W, _stream()), "sub_spatial_mean")
+    return out
+
+
+def channel_l2norm(x, out=None):
+    B, C, H, W = x.shape
+    if out is None:
+        out = _new(x, 1, H, W)
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    _lib.check(_lib.load().irr_channel_l2norm_fwd(px, sx, po, so, B, C, H * W, _stream()), "channel_l2norm")
+    return out
+
+
+def refine_gather(logits, src, out=None):
+    B, C, H, W = src.shape
+    assert logits.shape == (B, 9, H, W)
+    if out is None:
+        out = _new(src, C, H, W)
+    pl, sl = _v(logits, "logits"); ps, ss = _v(src, "src"); po, so = _v(out, "out")
+    _lib.check(_lib.load().irr_refine_gather_fwd(pl, sl, ps, ss, po, so, B, C, H, W, _stream()), "refine_gather")
+    return out

@@ -1,0 +1,240 @@
+"""Op-level parity of the C-ABI kernels against the oracle (numpy / torch-CPU restatements pinned to the reference)
+and against the committed golden vectors.  Tolerances: 1e-4 abs (north_star) for values — tighter where the op is a
+pure gather — and BITWISE for the warp validity mask."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import irr_oracle as O
+from oracle import ops_np as N
+
+pytestmark = pytest.mark.gpu
+
+
+def rs(seed, shape, kind="normal"):
+    r = np.random.RandomState(seed)
+    a = r.standard_normal(shape) if kind == "normal" else np.abs(r.standard_normal(shape)) * 0.3
+    return a.astype("float32")
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+# ------------------------------------------------------------------ cost volume
+CV_SHAPES = [(1, 64, 64, 128), (2, 196, 7, 16), (2, 32, 109, 256), (1, 96, 24, 78), (1, 3, 5, 5), (3, 17, 9, 13)]
+
+
+@pytest.mark.parametrize("si", range(len(CV_SHAPES)))
+@pytest.mark.parametrize("kind", ["normal", "lrelu"])
+def test_cost_volume_golden(cuda, golden_dir, si, kind):
+    from irr_b200 import ops
+    g = np.load(f"{golden_dir}/cost_volume.npz")
+    shape = CV_SHAPES[si]
+    key = "x".join(map(str, shape)) + "_" + kind
+    seed = int(g[key + "__seed"])
+    f1, f2 = rs(seed, shape, kind), rs(seed + 1000, shape, kind)
+    out = ops.correlation(dev(f1, cuda), dev(f2, cuda)).cpu().numpy()
+    sub = out if out.size <= 60000 else out[:, :, ::5, ::7]
+    assert np.abs(sub - g[key + "__sub"]).max() <= 1e-4
+    np.testing.assert_allclose(out.sum(axis=(2, 3), dtype=np.float64), g[key + "__sum"], atol=2e-2, rtol=1e-4)
+    # full tensor vs the numpy oracle
+    assert np.abs(out - N.cost_volume_np(f1, f2)).max() <= 1e-4
+
+
+def test_cost_volume_analytic(cuda):
+    """Delta images prove channel order (dy+4)*9+(dx+4); constant images prove zero padding and the /C."""
+    from irr_b200 import ops
+    C, H, W = 5, 12, 40
+    f1 = np.zeros((1, C, H, W), "float32"); f2 = np.zeros((1, C, H, W), "float32")
+    f1[0, 2, 6, 20] = 3.0
+    f2[0, 2, 6 + 2, 20 - 3] = 5.0  # dy=+2, dx=-3
+    out = ops.correlation(dev(f1, cuda), dev(f2, cuda)).cpu().numpy()
+    ch = (2 + 4) * 9 + (-3 + 4)
+    assert out[0, ch, 6, 20] == pytest.approx(15.0 / C)
+    out[0, ch, 6, 20] = 0
+    assert np.abs(out).max() == 0
+    ones = np.ones((1, C, H, W), "float32")
+    out = ops.correlation(dev(ones, cuda), dev(ones, cuda)).cpu().numpy()
+    assert out[0, 40, 5, 5] == pytest.approx(1.0)
+    assert out[0, 0, 0, 0] == 0.0 and out[0, 80, H - 1, W - 1] == 0.0  # (dy,dx)=(-4,-4) at the top-left corner
+    assert out[0, 80, 0, 0] == pytest.approx(1.0)
+
+
+def test_cost_volume_slice_shift_lrelu(cuda):
+    """Write into a channel slice of a bigger buffer, rotate the f2 batch, fuse LeakyReLU."""
+    from irr_b200 import ops
+    B, C, H, W = 4, 32, 28, 64
+    f = rs(1, (B, C, H, W))
+    ft = dev(f, cuda)
+    buf = torch.full((B, 120, H, W), 7.0, device=cuda)
+    ops.correlation(ft, ft, out=buf[:, 10:91], shift=2, slope=0.1)
+    ref = N.cost_volume_np(f, np.roll(f, -2, axis=0))
+    ref = np.where(ref > 0, ref, ref * np.float32(0.1))
+    got = buf.cpu().numpy()
+    assert np.abs(got[:, 10:91] - ref).max() <= 1e-4
+    assert (got[:, :10] == 7.0).all() and (got[:, 91:] == 7.0).all()
+
+
+def test_correlation_generic_vs_c_oracle(cuda):
+    from irr_b200 import ops
+    f1, f2 = rs(5, (2, 6, 20, 24)), rs(6, (2, 6, 20, 24))
+    for (pad, k, md, s1, s2) in [(4, 1, 4, 1, 1), (20, 1, 20, 1, 2), (3, 3, 2, 2, 1), (4, 1, 4, 1, 2)]:
+        ref = N.corr_ref_c(f1, f2, pad, k, md, s1, s2)
+        got = ops.correlation_generic(dev(f1, cuda), dev(f2, cuda), pad, k, md, s1, s2).cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-5
+
+
+# ------------------------------------------------------------------ warp
+@pytest.mark.parametrize("ci", range(5))
+def test_warp_golden_mask_bitexact(cuda, golden_dir, ci):
+    from irr_b200 import ops
+    ops.set_grid_mode(ops.GRID_TRUE_DIV)
+    g = np.load(f"{golden_dir}/warp.npz")
+    seed, B, C, H, W, him, wim = [int(v) for v in g[f"case{ci}__meta"]]
+    x = rs(seed, (B, C, H, W))
+    flow = g[f"case{ci}__flow"]
+    lx, ly = dev(g[f"case{ci}__lin_x"], cuda), dev(g[f"case{ci}__lin_y"], cuda)
+    mask = torch.empty((B, H, W), device=cuda)
+    out = ops.warp(dev(x, cuda), dev(flow, cuda), him, wim, 0.05, mask_out=mask, lin_x=lx, lin_y=ly)
+    assert (mask.cpu().numpy() != g[f"case{ci}__mask"]).sum() == 0  # bitwise
+    assert np.abs(out.cpu().numpy() - g[f"case{ci}__out"]).max() <= 2e-6
+
+
+def test_warp_identity_and_minuend(cuda):
+    from irr_b200 import ops
+    x = rs(11, (2, 7, 13, 39))
+    xt = dev(x, cuda)
+    zero = torch.zeros((2, 2, 13, 39), device=cuda)
+    mask = torch.empty((2, 13, 39), device=cuda)
+    out = ops.warp(xt, zero, 375, 1242, 0.05, mask_out=mask)
+    assert (mask == 1).all()
+    assert (out - xt).abs().max().item() <= 1e-6
+    d = ops.warp(xt, zero, 375, 1242, 0.05, minuend=xt, shift=1)
+    ref = x - np.roll(x, -1, axis=0)
+    assert np.abs(d.cpu().numpy() - ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("mode", ["true_div", "recip"])
+def test_warp_matches_torch_device_ops(cuda, mode):
+    """TRUE_DIV reproduces the reference run on the CPU; RECIP_MUL reproduces the reference's torch ops run on THIS
+    GPU (torch's CUDA `tensor / scalar` multiplies by the reciprocal).  Mask must be bit-identical in both."""
+    from irr_b200 import ops
+    B, C, H, W, him, wim = 2, 8, 55, 128, 436, 1024
+    x = torch.from_numpy(rs(21, (B, C, H, W)))
+    flow = torch.from_numpy(rs(22, (B, 2, H, W))) * torch.tensor([wim / W, him / H]).view(1, 2, 1, 1) * 0.05 * 6.0
+    if mode == "true_div":
+        ops.set_grid_mode(ops.GRID_TRUE_DIV)
+        grid = O.sampling_grid(flow, him, wim, 0.05)
+        ref = O.warp(x, flow, him, wim, 0.05)
+        m = (torch.nn.functional.grid_sample(torch.ones_like(x), grid, align_corners=True) >= 1.0)[:, 0]
+    else:
+        ops.set_grid_mode(ops.GRID_RECIP_MUL)
+        xg, fg = x.to(cuda), flow.to(cuda)
+        grid = O.sampling_grid(fg, him, wim, 0.05)
+        ref = O.warp(xg, fg, him, wim, 0.05).cpu()
+        m = (torch.nn.functional.grid_sample(torch.ones_like(xg), grid, align_corners=True) >= 1.0)[:, 0].cpu()
+    try:
+        mask = torch.empty((B, H, W), device=cuda)
+        out = ops.warp(x.to(cuda), flow.to(cuda), him, wim, 0.05, mask_out=mask)
+    finally:
+        ops.set_grid_mode(ops.GRID_TRUE_DIV)
+    nbad = int((mask.cpu() != m.float()).sum())
+    assert nbad == 0, f"{nbad} mask pixels differ ({mode})"
+    assert (out.cpu() - ref).abs().max().item() <= 2e-6
+
+
+def test_warp_correlation_fused_equals_unfused(cuda):
+    from irr_b200 import ops
+    B, C, H, W, him, wim = 4, 32, 28, 64, 436, 1024
+    f = dev(rs(31, (B, C, H, W)), cuda)
+    flow = dev(rs(32, (B, 2, H, W)), cuda) * torch.tensor([wim / W, him / H], device=cuda).view(1, 2, 1, 1) * 0.05 * 3.0
+    fused = ops.warp_correlation(f, f, flow, him, wim, 0.05, shift=2, slope=0.1)
+    w = ops.warp(f, flow, him, wim, 0.05, shift=2)
+    unfused = ops.correlation(f, w, slope=0.1)
+    assert (fused - unfused).abs().max().item() <= 1e-6
+    # and against the oracle on the CPU
+    fc, flc = f.cpu(), flow.cpu()
+    ref = torch.nn.functional.leaky_relu(O.cost_volume(fc, O.warp(torch.roll(fc, -2, 0), flc, him, wim, 0.05)), 0.1)
+    assert (fused.cpu() - ref).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------------------ conv
+CONV_CASES = [
+    # (B, Cin, H, W, Cout, k, stride, dil)
+    (2, 3, 64, 96, 16, 3, 2, 1), (2, 16, 32, 48, 16, 3, 1, 1), (1, 128, 14, 32, 196, 3, 2, 1),
+    (2, 115, 28, 64, 128, 3, 1, 1), (1, 563, 14, 32, 2, 3, 1, 1), (1, 565, 28, 64, 128, 3, 1, 1),
+    (1, 128, 28, 64, 128, 3, 1, 2), (1, 128, 28, 64, 96, 3, 1, 8), (1, 96, 28, 64, 64, 3, 1, 16),
+    (2, 196, 7, 16, 32, 1, 1, 1), (1, 16, 47, 156, 3, 1, 1, 1), (1, 35, 13, 39, 128, 3, 1, 1),
+    (1, 32, 21, 37, 9, 3, 1, 1), (1, 11, 47, 155, 32, 3, 1, 1), (1, 32, 24, 78, 1, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_vs_torch_cpu(cuda, case):
+    from irr_b200 import ops
+    B, Cin, H, W, Cout, k, s, d = case
+    x = torch.from_numpy(rs(41, (B, Cin, H, W)))
+    w = torch.from_numpy(rs(42, (Cout, Cin, k, k))) * float(np.sqrt(2.0 / (Cin * k * k)))
+    b = torch.from_numpy(rs(43, (Cout,))) * 0.1
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x, w, b, stride=s, padding=((k - 1) * d) // 2, dilation=d), 0.1)
+    packed = ops.pack_weights(w.to(cuda))
+    got = ops.conv2d(x.to(cuda), packed, b.to(cuda), Cout, k, s, d, slope=0.1)
+    assert got.shape == ref.shape
+    assert (got.cpu() - ref).abs().max().item() <= 1e-4
+
+
+def test_conv2d_slices_addend_alpha(cuda):
+    """Dense-block style: read a channel suffix of the concat buffer, write a slice, y = addend + alpha*(conv+b)."""
+    from irr_b200 import ops
+    B, Ct, H, W = 2, 60, 20, 36
+    buf = torch.from_numpy(rs(51, (B, Ct, H, W))).to(cuda)
+    w = torch.from_numpy(rs(52, (24, 40, 3, 3))) * 0.05
+    b = torch.from_numpy(rs(53, (24,))) * 0.1
+    add = torch.from_numpy(rs(54, (B, 24, H, W))).to(cuda)
+    xin = buf[:, 20:60].cpu()
+    ref = add.cpu() + 0.1 * torch.nn.functional.conv2d(xin, w, b, padding=1)
+    before = buf.clone()
+    out = torch.zeros((B, 30, H, W), device=cuda)
+    ops.conv2d(buf[:, 20:60], ops.pack_weights(w.to(cuda)), b.to(cuda), 24, 3, slope=1.0, out=out[:, 3:27],
+               addend=add, alpha=0.1)
+    assert (out[:, 3:27].cpu() - ref).abs().max().item() <= 1e-4
+    assert (out[:, :3] == 0).all() and (out[:, 27:] == 0).all() and torch.equal(buf, before)
+
+
+# ------------------------------------------------------------------ small ops
+def test_resize_scale_nearest(cuda, golden_dir):
+    from irr_b200 import ops
+    g = np.load(f"{golden_dir}/modules.npz")
+    t = rs(310, (2, 2, 7, 16))
+    a = ops.resize_ac(dev(t, cuda), 14, 32).cpu().numpy()
+    b = ops.resize_ac(dev(t, cuda), 13, 39).cpu().numpy()
+    assert np.abs(a - g["resize_ac__out"]).max() <= 1e-6 and np.abs(b - g["resize_ac__odd"]).max() <= 1e-6
+    c = ops.resize_ac(dev(t, cuda), 13, 39, s_even=2.0, s_odd=3.0).cpu().numpy()
+    assert np.abs(c[:, 0] - 2 * b[:, 0]).max() <= 1e-6 and np.abs(c[:, 1] - 3 * b[:, 1]).max() <= 1e-6
+    # down-sizing (image pyramid for the refinement input, IRR_PWC.py:126-127)
+    img = rs(311, (1, 3, 94, 156))
+    ref = torch.nn.functional.interpolate(torch.from_numpy(img), size=[24, 39], mode="bilinear", align_corners=True)
+    assert (ops.resize_ac(dev(img, cuda), 24, 39).cpu() - ref).abs().max().item() <= 1e-6
+    s = ops.scale_channels(dev(t, cuda), s_even=0.5, s_odd=-2.0).cpu().numpy()
+    assert np.array_equal(s[:, 0], t[:, 0] * np.float32(0.5)) and np.array_equal(s[:, 1], t[:, 1] * np.float32(-2))
+    o = rs(312, (2, 1, 12, 20))
+    for (oh, ow) in [(24, 40), (23, 39), (24, 39)]:
+        like = torch.zeros(1, 1, oh, ow)
+        ref = O.upsample_x2(torch.from_numpy(o), like)
+        got = ops.upsample_nearest2x(dev(o, cuda), oh, ow).cpu()
+        assert (got - ref).abs().max().item() <= 1e-6
+
+
+def test_refine_pieces(cuda):
+    from irr_b200 import ops
+    fl = torch.from_numpy(rs(61, (2, 2, 14, 22)))
+    ref = fl - fl.mean(2).mean(2)[:, :, None, None]
+    assert (ops.sub_spatial_mean(fl.to(cuda)).cpu() - ref).abs().max().item() <= 1e-6
+    d = torch.from_numpy(rs(62, (2, 3, 14, 22)))
+    assert (ops.channel_l2norm(d.to(cuda)).cpu() - torch.norm(d, p=2, dim=1, keepdim=True)).abs().max().item() <= 1e-6
+    logits = torch.from_numpy(rs(63, (2, 9, 14, 22))) * 2
+    ref = O._kernel_gather(fl, logits)
+    assert (ops.refine_gather(logits.to(cuda), fl.to(cuda)).cpu() - ref).abs().max().item() <= 1e-5
