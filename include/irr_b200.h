@@ -99,6 +99,8 @@ int irr_correlation_generic_out_shape(int H, int W, int pad_size, int kernel_siz
  * x: B x Cin x H x W slice, y: B x Cout x Ho x Wo slice, Ho = floor((H + 2*pad - dil*(k-1) - 1)/stride) + 1.
  * w_packed: produced by irr_conv2d_pack_weights for the same `math`. */
 size_t irr_conv2d_packed_bytes(int Cout, int Cin, int ksize, int math);
+/* 1 if `math` can run this layer shape, 0 otherwise (the CUDA-core mode runs every k in {1,3} shape). */
+int irr_conv2d_math_supported(int Cout, int Cin, int ksize, int stride, int dilation, int math);
 int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int Cin, int ksize, int math,
                             irr_stream_t stream);
 int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,

@@ -1,0 +1,201 @@
+"""IRR-PWC (bi-directional flow + occlusion, shared-weight iterative residual refinement) — eval-mode forward.
+
+Drop-in for the reference's ``models/IRR_PWC.py`` ``PWCNet``: same constructor ``(args, div_flow=0.05)``, same
+sub-module / parameter names (so ``saved_check_point/pwcnet/IRR-PWC_*`` load unchanged), same
+``forward({'input1','input2'}) -> {'flow','occ'}`` contract (IRR_PWC.py:51-184, eval branch :176-184).
+
+What is different is HOW the level loop (IRR_PWC.py:73-174) is executed:
+  * the forward and backward directions are one 2B batch ([x1;x2] paired with [x2;x1] through a batch rotation inside
+    the warp / correlation kernels) — half the launches, twice the parallelism at the 7x16 ... 28x64 levels;
+  * the feature pyramid runs once on the 2B batch (the reference runs the extractor twice, IRR_PWC.py:58-59);
+  * warp + mask + cost volume + LeakyReLU are ONE kernel writing straight into the estimator's input buffer;
+  * every torch.cat of the dense blocks / context / refinement inputs is a channel slice of a pre-allocated buffer;
+  * residual adds, the *0.1 of the occlusion up-sampler and the flow/occ skip connections are conv epilogues;
+  * the as-executed flow scaling (rescale_flow mutates its argument at IRR_PWC.py:128-129) is
+    written out explicitly: RefineFlow consumes ``flow_cont`` in GLOBAL units.
+Training mode (per-level output lists) is out of scope.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .irr_modules import OccUpsampleNetwork, RefineFlow, RefineOcc
+from .pwc_modules import (ContextNetwork, FeatureExtractor, FlowEstimatorDense, OccContextNetwork, OccEstimatorDense,
+                          WarpingLayer, conv, flow_scales, initialize_msra)
+
+
+class PWCNet(nn.Module):
+    def __init__(self, args=None, div_flow=0.05):
+        super().__init__()
+        self.args = args
+        self._div_flow = div_flow
+        self.search_range = 4
+        self.num_chs = [3, 16, 32, 64, 96, 128, 196]
+        self.output_level = 4
+        self.num_levels = 7
+        self.leakyRELU = nn.LeakyReLU(0.1, inplace=True)
+
+        self.feature_pyramid_extractor = FeatureExtractor(self.num_chs)
+        self.warping_layer = WarpingLayer()
+
+        self.dim_corr = (self.search_range * 2 + 1) ** 2
+        self.num_ch_in_flo = self.dim_corr + 32 + 2
+        self.num_ch_in_occ = self.dim_corr + 32 + 1
+
+        self.flow_estimators = FlowEstimatorDense(self.num_ch_in_flo)
+        self.context_networks = ContextNetwork(self.num_ch_in_flo + 448 + 2)
+        self.occ_estimators = OccEstimatorDense(self.num_ch_in_occ)
+        self.occ_context_networks = OccContextNetwork(self.num_ch_in_occ + 448 + 1)
+        self.occ_shuffle_upsample = OccUpsampleNetwork(11, 1)
+
+        self.conv_1x1 = nn.ModuleList([conv(196, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(128, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(96, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(64, 32, kernel_size=1, stride=1, dilation=1)])
+        self.conv_1x1_1 = conv(16, 3, kernel_size=1, stride=1, dilation=1)
+
+        self.refine_flow = RefineFlow(2 + 1 + 32)
+        self.refine_occ = RefineOcc(1 + 32 + 32)
+        self.corr_params = {"pad_size": self.search_range, "kernel_size": 1, "max_disp": self.search_range,
+                            "stride1": 1, "stride2": 1, "corr_multiply": 1}
+        initialize_msra(self.modules())
+
+    # ------------------------------------------------------------------------------------------------ stages
+    def estimator_level(self, l, feat, flow_up, occ_up, imgs, height_im, width_im, record=None):
+        """One pass of IRR_PWC.py:75-147 for pyramid level l <= 4 on the 2B batch.
+
+        feat   : (2B, C_l, h, w)  rows [0,B) = x1 features, rows [B,2B) = x2 features
+        flow_up: (2B, 2, h, w) flow in GLOBAL units already resized to this level (zeros at l == 0); rows [0,B) forward
+        occ_up : (2B, 1, h, w)
+        imgs   : (2B, 3, H, W)
+        returns (flow, occ) for this level (flow in GLOBAL units), each on the 2B batch."""
+        B2, C, h, w = feat.shape
+        B = B2 // 2
+        dev = feat.device
+        df = self._div_flow
+        nf, no = self.num_ch_in_flo, self.num_ch_in_occ  # 115, 114
+        rec = (lambda k, v: record.__setitem__(k, v.clone())) if record is not None else (lambda k, v: None)
+
+        # estimator input buffers: [448 dense outputs | corr 81 | x_1by1 32 | flow 2 or occ 1 | est 2 or 1]
+        buf_f = torch.empty((B2, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
+        buf_o = torch.empty((B2, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
+        corr = buf_f[:, 448:529]
+        if l == 0:  # IRR_PWC.py:78-80,90-95 — no warp at the coarsest level
+            ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
+        else:       # :86-95 fused
+            ops.warp_correlation(feat, feat, flow_up, height_im, width_im, df, out=corr, shift=B, slope=0.1)
+        x1by1 = buf_f[:, 529:561]
+        if l != self.output_level:  # :97-102
+            self.conv_1x1[l](feat, out=x1by1)
+        else:
+            ops.scale_channels(feat, out=x1by1)
+        ops.scale_channels(buf_f[:, 448:561], out=buf_o[:, 448:561])  # shared [corr | x_1by1] block
+        su_l, sv_l = flow_scales(h, w, df, width_im, height_im, True)
+        ops.scale_channels(flow_up, out=buf_f[:, 561:563], s_even=su_l, s_odd=sv_l)  # :105-106 to_local
+        ops.scale_channels(occ_up, out=buf_o[:, 561:562])
+        rec("corr", corr); rec("x_1by1", x1by1)
+
+        # flow: dense estimator + residual (:108-111), context + residual (:113-114)
+        self.flow_estimators.forward_into(buf_f, out=buf_f[:, 563:565], addend=buf_f[:, 561:563])
+        rec("flow_est", buf_f[:, 563:565])
+        flow_cont = self.context_networks(buf_f, addend=buf_f[:, 563:565])
+        rec("flow_cont", flow_cont)
+        # occlusion (:117-123)
+        self.occ_estimators.forward_into(buf_o, out=buf_o[:, 562:563], addend=buf_o[:, 561:562])
+        occ_cont = self.occ_context_networks(buf_o, addend=buf_o[:, 562:563])
+        rec("occ_cont", occ_cont)
+
+        flow = self.refine_flow_stage(flow_cont, x1by1, imgs, height_im, width_im)
+        rec("flow", flow)
+        occ = self.refine_occ_stage(occ_cont, x1by1, flow, height_im, width_im)
+        rec("occ", occ)
+        return flow, occ
+
+    def refine_flow_stage(self, flow_cont, x1by1, imgs, height_im, width_im):
+        """IRR_PWC.py:126-138.  ``flow_cont`` arrives in LOCAL units and is converted IN PLACE to global units first —
+        exactly what the un-rebound rescale_flow call at :128-129 leaves behind, so RefineFlow (:132-133)
+        sees global units; its output is then scaled to global once more (:137-138)."""
+        B2, _, h, w = flow_cont.shape
+        B = B2 // 2
+        df = self._div_flow
+        su_g, sv_g = flow_scales(h, w, df, width_im, height_im, False)
+        img_r = ops.resize_ac(imgs, h, w)  # :126-127
+        ops.scale_channels(flow_cont, out=flow_cont, s_even=su_g, s_odd=sv_g)
+        rf_in = torch.empty((B2, 35, h, w), dtype=torch.float32, device=flow_cont.device)
+        diff = ops.warp(img_r, flow_cont, height_im, width_im, df, minuend=img_r, shift=B)  # img_a - warp(img_b)
+        ops.sub_spatial_mean(flow_cont, out=rf_in[:, 0:2])
+        ops.channel_l2norm(diff, out=rf_in[:, 2:3])
+        ops.scale_channels(x1by1, out=rf_in[:, 3:35])
+        flow = self.refine_flow.gather(rf_in, flow_cont)
+        ops.scale_channels(flow, out=flow, s_even=su_g, s_odd=sv_g)
+        return flow
+
+    def refine_occ_stage(self, occ_cont, x1by1, flow, height_im, width_im):
+        """IRR_PWC.py:141-145: occ = RefineOcc(occ_cont, x_1by1, x_1by1 - warp(other x_1by1, flow))."""
+        B2, _, h, w = occ_cont.shape
+        B = B2 // 2
+        ro_in = torch.empty((B2, 65, h, w), dtype=torch.float32, device=occ_cont.device)
+        ops.scale_channels(occ_cont, out=ro_in[:, 0:1])
+        ops.scale_channels(x1by1, out=ro_in[:, 1:33])
+        ops.warp(x1by1, flow, height_im, width_im, self._div_flow, minuend=x1by1, shift=B, out=ro_in[:, 33:65])
+        return self.refine_occ.gather(ro_in, occ_cont)
+
+    def upsample_level(self, l, feat, flow, occ_prev, height_im, width_im, record=None):
+        """IRR_PWC.py:150-174 for l in {5, 6}: occlusion up-sampling guided by warped features / flows."""
+        B2, C, h, w = feat.shape
+        B = B2 // 2
+        df = self._div_flow
+        x_in = torch.empty((B2, 11, h, w), dtype=torch.float32, device=feat.device)
+        ops.upsample_nearest2x(occ_prev, h, w, out=x_in[:, 0:1])
+        if l != self.num_levels - 1:  # :160-164
+            self.conv_1x1_1(feat, out=x_in[:, 1:4])
+            xw = ops.warp(feat, flow, height_im, width_im, df, shift=B)
+            self.conv_1x1_1(xw, out=x_in[:, 4:7])
+        else:
+            ops.scale_channels(feat, out=x_in[:, 1:4])
+            ops.warp(feat, flow, height_im, width_im, df, shift=B, out=x_in[:, 4:7])
+        ops.scale_channels(flow, out=x_in[:, 7:9])
+        ops.warp(flow, flow, height_im, width_im, df, shift=B, out=x_in[:, 9:11])  # flow_b warped by flow_f, and v.v.
+        occ = self.occ_shuffle_upsample.forward_into(x_in)
+        if record is not None:
+            record["occ"] = occ.clone()
+        return occ
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, input_dict, record=None):
+        if self.training:
+            raise RuntimeError("irr_b200.IRR_PWC: only the eval-mode forward is implemented (call .eval())")
+        x1_raw = input_dict['input1']
+        x2_raw = input_dict['input2']
+        B, _, height_im, width_im = x1_raw.shape
+        with torch.no_grad():
+            imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()  # (2B, 3, H, W)
+            pyramid = self.feature_pyramid_extractor(imgs) + [imgs]
+            flow = occ = None
+            for l, feat in enumerate(pyramid):
+                _, _, h, w = feat.shape
+                rec_l = None
+                if record is not None:
+                    rec_l = {}
+                    record[l] = rec_l
+                if l <= self.output_level:
+                    if l == 0:
+                        flow_up = torch.zeros((2 * B, 2, h, w), dtype=torch.float32, device=imgs.device)
+                        occ_up = torch.zeros((2 * B, 1, h, w), dtype=torch.float32, device=imgs.device)
+                    else:
+                        flow_up = ops.resize_ac(flow, h, w)
+                        occ_up = ops.resize_ac(occ, h, w)
+                    if rec_l is not None:
+                        rec_l["feat"] = feat.clone(); rec_l["flow_up"] = flow_up.clone(); rec_l["occ_up"] = occ_up.clone()
+                    flow, occ = self.estimator_level(l, feat, flow_up, occ_up, imgs, height_im, width_im, rec_l)
+                else:
+                    flow = ops.resize_ac(flow, h, w)
+                    if rec_l is not None:
+                        rec_l["feat"] = feat.clone(); rec_l["flow_up"] = flow.clone(); rec_l["occ_in"] = occ.clone()
+                    occ = self.upsample_level(l, feat, flow, occ, height_im, width_im, rec_l)
+            out_flow = ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / self._div_flow,
+                                     s_odd=1.0 / self._div_flow)  # :176
+            out_occ = ops.resize_ac(occ[:B], height_im, width_im)  # :177
+        return {'flow': out_flow, 'occ': out_occ}

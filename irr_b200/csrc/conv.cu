@@ -27,6 +27,13 @@ size_t irr_conv2d_packed_bytes(int Cout, int Cin, int ksize, int math) {
   return 0;
 }
 
+int irr_conv2d_math_supported(int Cout, int Cin, int ksize, int stride, int dilation, int math) {
+  if (Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3) || stride < 1 || dilation < 1) return 0;
+  if (math == IRR_MATH_FP32_SIMT) return 1;
+  if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32) return tc_supported(Cout, Cin, ksize, stride, dilation) ? 1 : 0;
+  return 0;
+}
+
 int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int Cin, int ksize, int math,
                             irr_stream_t stream) {
   const char* fn = "irr_conv2d_pack_weights";

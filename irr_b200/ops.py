@@ -137,6 +137,10 @@ def conv_out_hw(H: int, W: int, ks: int, stride: int, dil: int) -> Tuple[int, in
     return (H + 2 * pad - dil * (ks - 1) - 1) // stride + 1, (W + 2 * pad - dil * (ks - 1) - 1) // stride + 1
 
 
+def tc_supported(Cout, Cin, ks, stride, dil, math: int = MATH_TC_3XTF32) -> bool:
+    return bool(_lib.load().irr_conv2d_math_supported(Cout, Cin, ks, stride, dil, math))
+
+
 def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
     Cout, Cin, ks, ks2 = w.shape
     assert ks == ks2

@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's ``models/pwc_modules.py`` for the inference path.
+
+Same public names, constructor arguments, ``forward()`` signatures and parameter names (so the reference's
+checkpoints load unchanged); the arithmetic is the hand-written sm_100a library behind
+``irr_b200.ops``.  nn.Conv2d / nn.LeakyReLU objects are kept as *parameter holders* only — their library
+forward is never executed.  There is no non-CUDA path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_default_math = ops.MATH_FP32_SIMT
+
+
+def set_conv_math(math: int) -> None:
+    """Process-wide default arithmetic for conv blocks (ops.MATH_*); layers the tensor-core path cannot take
+    fall back to the CUDA-core kernel *inside the native library's dispatch table*, never to PyTorch."""
+    global _default_math
+    _default_math = math
+
+
+def get_conv_math() -> int:
+    return _default_math
+
+
+class ConvBlock(nn.Sequential):
+    """``conv()`` of models/pwc_modules.py:8-19: [Conv2d(bias, pad=((k-1)*dil)//2), LeakyReLU(0.1)?].
+
+    forward(x, out=None, addend=None, alpha=1.0) computes  addend + alpha * act(conv(x) + bias)  with our kernel,
+    optionally straight into a channel slice ``out`` of a larger buffer."""
+
+    def __init__(self, in_planes, out_planes, kernel_size=3, stride=1, dilation=1, isReLU=True):
+        mods = [nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, dilation=dilation,
+                          padding=((kernel_size - 1) * dilation) // 2, bias=True)]
+        if isReLU:
+            mods.append(nn.LeakyReLU(0.1, inplace=True))
+        super().__init__(*mods)
+        self.cin, self.cout, self.ks, self.stride, self.dil = in_planes, out_planes, kernel_size, stride, dilation
+        self.slope = 0.1 if isReLU else 1.0
+        self._packed = {}  # math -> (key, packed tensor)
+
+    def _math(self):
+        m = _default_math
+        if m != ops.MATH_FP32_SIMT and not ops.tc_supported(self.cout, self.cin, self.ks, self.stride, self.dil):
+            m = ops.MATH_FP32_SIMT
+        return m
+
+    def packed(self, math):
+        w = self[0].weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        hit = self._packed.get(math)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.pack_weights(w, math))
+            self._packed[math] = hit
+        return hit[1]
+
+    def forward(self, x, out=None, addend=None, alpha=1.0):
+        math = self._math()
+        return ops.conv2d(x, self.packed(math), self[0].bias, self.cout, self.ks, self.stride, self.dil,
+                          slope=self.slope, out=out, addend=addend, alpha=alpha, math=math)
+
+
+def conv(in_planes, out_planes, kernel_size=3, stride=1, dilation=1, isReLU=True):
+    return ConvBlock(in_planes, out_planes, kernel_size, stride, dilation, isReLU)
+
+
+def initialize_msra(modules):
+    """models/pwc_modules.py:22-39."""
+    for layer in modules:
+        if isinstance(layer, (nn.Conv2d, nn.ConvTranspose2d)):
+            nn.init.kaiming_normal_(layer.weight)
+            if layer.bias is not None:
+                nn.init.constant_(layer.bias, 0)
+
+
+def compute_cost_volume(feat1, feat2, param_dict):
+    """models/pwc_modules.py:42-62 (kernel_size=1, stride1=stride2=1); only ``max_disp`` is read, as there."""
+    return ops.correlation(feat1, feat2, max_disp=param_dict["max_disp"])
+
+
+def upsample2d_as(inputs, target_as, mode="bilinear"):
+    """models/pwc_modules.py:65-67."""
+    assert mode == "bilinear"
+    _, _, h, w = target_as.size()
+    return ops.resize_ac(inputs, h, w)
+
+
+def flow_scales(h, w, div_flow, width_im, height_im, to_local=True):
+    """The Python-double scale factors of rescale_flow (models/pwc_modules.py:71-76)."""
+    if to_local:
+        return float(w / width_im / div_flow), float(h / height_im / div_flow)
+    return float(width_im * div_flow / w), float(height_im * div_flow / h)
+
+
+def rescale_flow(flow, div_flow, width_im, height_im, to_local=True):
+    """models/pwc_modules.py:70-82, including its in-place side effect on ``flow``: the argument is
+    scaled in place AND a new tensor with the same values is returned."""
+    su, sv = flow_scales(flow.size(2), flow.size(3), div_flow, width_im, height_im, to_local)
+    ops.scale_channels(flow, out=flow, s_even=su, s_odd=sv)
+    return flow.clone()
+
+
+class FeatureExtractor(nn.Module):
+    """models/pwc_modules.py:85-104."""
+
+    def __init__(self, num_chs):
+        super().__init__()
+        self.num_chs = num_chs
+        self.convs = nn.ModuleList()
+        for ch_in, ch_out in zip(num_chs[:-1], num_chs[1:]):
+            self.convs.append(nn.Sequential(conv(ch_in, ch_out, stride=2), conv(ch_out, ch_out)))
+
+    def forward(self, x):
+        pyramid = []
+        for pair in self.convs:
+            x = pair[1](pair[0](x))
+            pyramid.append(x)
+        return pyramid[::-1]
+
+
+def get_grid(x):
+    """models/pwc_modules.py:107-112 — kept for API parity (the kernels take the two 1-D vectors instead)."""
+    B, _, H, W = x.shape
+    gx = ops.host_linspace(W, x.device).view(1, 1, 1, W).expand(B, 1, H, W)
+    gy = ops.host_linspace(H, x.device).view(1, 1, H, 1).expand(B, 1, H, W)
+    return torch.cat([gx, gy], 1)
+
+
+class WarpingLayer(nn.Module):
+    """models/pwc_modules.py:115-133."""
+
+    def forward(self, x, flow, height_im, width_im, div_flow):
+        return ops.warp(x, flow, height_im, width_im, div_flow)
+
+
+class _DenseEstimator(nn.Module):
+    """FlowEstimatorDense / OccEstimatorDense (models/pwc_modules.py:153-170,190-207).
+
+    The reference re-concatenates after every conv (x_{i} = cat[conv_i(x_{i-1}), x_{i-1}]).  Here the whole block lives
+    in ONE buffer laid out as the final x5 = [conv5 | conv4 | conv3 | conv2 | conv1 | x]; conv_i reads the channel
+    suffix that already exists and writes its slice in front of it, so no copy is ever made."""
+
+    GROWTH = [128, 128, 96, 64, 32]
+
+    def __init__(self, ch_in, ch_out):
+        super().__init__()
+        self.ch_in, self.ch_out = ch_in, ch_out
+        self.conv1 = conv(ch_in, 128)
+        self.conv2 = conv(ch_in + 128, 128)
+        self.conv3 = conv(ch_in + 256, 96)
+        self.conv4 = conv(ch_in + 352, 64)
+        self.conv5 = conv(ch_in + 416, 32)
+        self.conv_last = conv(ch_in + 448, ch_out, isReLU=False)
+
+    @property
+    def total_ch(self):
+        return self.ch_in + 448
+
+    def forward_into(self, buf, out=None, addend=None):
+        """``buf``: (B, >= ch_in+448, H, W) whose channels [448 : 448+ch_in] already hold the block input.
+        Fills channels [0:448]; returns conv_last(buf[:, :ch_in+448]) (+ addend) in ``out``."""
+        hi = 448
+        for c, g in zip([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5], self.GROWTH):
+            c(buf[:, hi:self.total_ch], out=buf[:, hi - g:hi])
+            hi -= g
+        return self.conv_last(buf[:, 0:self.total_ch], out=out, addend=addend)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        buf = torch.empty((B, self.total_ch, H, W), dtype=torch.float32, device=x.device)
+        ops.scale_channels(x, out=buf[:, 448:])
+        x_out = self.forward_into(buf)
+        return buf, x_out
+
+
+class FlowEstimatorDense(_DenseEstimator):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, 2)
+
+
+class OccEstimatorDense(_DenseEstimator):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, 1)
+
+
+class _Context(nn.Module):
+    """ContextNetwork / OccContextNetwork (models/pwc_modules.py:210-243): dilations 1,2,4,8,16,1,1."""
+
+    def __init__(self, ch_in, ch_out):
+        super().__init__()
+        self.convs = nn.Sequential(
+            conv(ch_in, 128, 3, 1, 1), conv(128, 128, 3, 1, 2), conv(128, 128, 3, 1, 4), conv(128, 96, 3, 1, 8),
+            conv(96, 64, 3, 1, 16), conv(64, 32, 3, 1, 1), conv(32, ch_out, isReLU=False))
+
+    def forward(self, x, out=None, addend=None):
+        for c in list(self.convs)[:-1]:
+            x = c(x)
+        return self.convs[-1](x, out=out, addend=addend)
+
+
+class ContextNetwork(_Context):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, 2)
+
+
+class OccContextNetwork(_Context):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, 1)
