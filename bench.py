@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — image-pairs/sec of the IRR-PWC inference hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph] [--math fp32|3xtf32|tf32]
+    N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+              bench.py --gpus N --steps K --warmup W
+
+One "step" = one full eval-mode IRR_PWC forward (BASELINE config 3: 1024x436, batch 8 per GPU, fp32, synthetic smooth
+image pairs, deterministic MSRA-like random weights).  Weak scaling: every rank runs its own batch of 8 pairs, there is no
+data-path collective; the only collective is one NCCL all-gather of the per-sample EPE after the timed region.
+
+Printed JSON (rank 0, one line): value = device-timed pairs/s with inputs resident in HBM (CUDA-graph replay of the
+level loop unless --no-graph); e2e = the same through the public nn.Module call with pinned HOST inputs, H2D and D2H
+copies inside the timed region; roofline = the correlation(+warp) kernel's achieved algorithmic HBM GB/s (per-launch
+CUDA events on the launching stream, an eager pass of the same steps) against MEASURED_PEAKS.json; roofline_conv = the
+conv stack's achieved FLOP/s; cpu_baseline = the oracle (torch-CPU restatement, bit-exact with the reference's Python)
+timed on this box's host cores on a bounded sample.  `--impl reference` times that CPU implementation alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H_IM, W_IM, BATCH = 436, 1024, 8
+METRIC = "image-pairs/sec IRR-PWC 1024x436 b8"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", 1400.0)), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def corr_bytes(B, C, H, W):  # B*H*W*(2*C*4 + 81*4); fused warp adds the flow read B*H*W*8
+    return B * H * W * (8 * C + 324)
+
+
+def conv_flops(meta):
+    B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math = meta
+    return 2.0 * B * Ho * Wo * Cout * Cin * ks * ks
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def cpu_forward_sample(steps, warmup, threads=None):
+    """Times the oracle (CPU restatement of the reference forward; oracle/irr_oracle.py) on a bounded sample:
+    one 1024x436 pair per step."""
+    from oracle import irr_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    p = O.synthetic_params("IRR_PWC", seed=1234, gain=0.7)
+    i1, i2, _ = O.synthetic_pair(1, H_IM, W_IM, seed=3, max_flow=20.0)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.irr_pwc_forward(p, i1, i2)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                ts.append(dt)
+    return ts
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    ts = cpu_forward_sample(steps, warm)
+    total = sum(ts)
+    value = len(ts) * 1.0 / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": warm, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "IRR_PWC full forward 1024x436 (BASELINE configs[2]); bounded sample: 1 pair per step",
+                   "per_gpu_batch": BATCH, "inputs": "smooth synthetic pair seed 3, MSRA-like weights seed 1234"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{len(ts)} x one 1024x436 pair through oracle/irr_oracle.py (torch CPU ops, bit-exact "
+                                   f"restatement of the reference forward; the reference itself is not on this box)"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--math", default=os.environ.get("IRR_MATH", "auto"), choices=["auto", "fp32", "3xtf32", "tf32"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import irr_b200
+    from irr_b200 import ops, pwc_modules
+    from oracle import irr_oracle as O  # parameters / synthetic inputs only (shared with the reference arm)
+
+    math = {"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32, "tf32": ops.MATH_TC_TF32}.get(args.math)
+    if math is None:  # auto: fp32-grade tensor-core path when the library has it, CUDA cores otherwise
+        math = ops.MATH_TC_3XTF32 if ops.tc_supported(128, 128, 3, 1, 1) else ops.MATH_FP32_SIMT
+    pwc_modules.set_conv_math(math)
+    math_name = {0: "fp32 CUDA-core FFMA", 1: "tcgen05 3xTF32 (fp32-grade)", 2: "tcgen05 TF32"}[math]
+
+    B = args.batch
+    model = irr_b200.IRR_PWC(None)
+    irr_b200.load_state_dict_strict(model, O.synthetic_params("IRR_PWC", seed=1234, gain=0.7))
+    model = model.to(dev).eval()
+    i1c, i2c, gtc = O.synthetic_pair(B, H_IM, W_IM, seed=3 + rank, max_flow=20.0)
+    h1, h2 = i1c.pin_memory(), i2c.pin_memory()
+    d1, d2 = h1.to(dev), h2.to(dev)
+    inp = {"input1": d1, "input2": d2}
+
+    # ---- warm-up (packs weights, fills the linspace cache), then optional CUDA-graph capture of the whole forward
+    for _ in range(2):
+        out = model(inp)
+    torch.cuda.synchronize()
+    ops.LAUNCHES = 0
+    out = model(inp)
+    launches_per_step = ops.LAUNCHES
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model(inp)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = model(inp)
+    step = (lambda: graph.replay()) if graph is not None else (lambda: model(inp))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the working set of one step (dense buffers ~2 GB at level 4) is >> the 126 MB L2, so nothing stays cached
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: public API, pinned host inputs -> H2D -> forward -> D2H of flow+occ, every step
+    oh_f = torch.empty((B, 2, H_IM, W_IM), dtype=torch.float32).pin_memory()
+    oh_o = torch.empty((B, 1, H_IM, W_IM), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        d1.copy_(h1, non_blocking=True)
+        d2.copy_(h2, non_blocking=True)
+        if graph is not None:
+            graph.replay()
+            o = out
+        else:
+            o = model(inp)
+        oh_f.copy_(o["flow"], non_blocking=True)
+        oh_o.copy_(o["occ"], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- per-kernel timing pass (eager, CUDA events on the launching stream around every launch)
+    ops.TIMING = []
+    nprof = min(args.steps, 3)
+    for _ in range(nprof):
+        model(inp)
+    torch.cuda.synchronize()
+    timing, ops.TIMING = ops.TIMING, None
+    agg = {}
+    for what, meta, s, e in timing:
+        agg.setdefault((what, meta), []).append(s.elapsed_time(e))
+    total_kernel_ms = sum(sum(v) for v in agg.values()) / nprof
+
+    # ---- metric reduction (the only collective): per-sample EPE vs the synthetic ground truth, all-gathered
+    epe_local = torch.norm(out["flow"] - gtc.to(dev), p=2, dim=1).mean(dim=(1, 2))
+    if dist is not None:
+        gathered = [torch.empty_like(epe_local) for _ in range(world)]
+        dist.all_gather(gathered, epe_local)
+        epe_all = torch.cat(gathered)
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    else:
+        epe_all = epe_local
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    pairs = B * world * args.steps
+    value = pairs / (ms * 1e-3)
+    # dominant correlation launch = the level-4 call (largest algorithmic bytes)
+    corr = [(k, v) for k, v in agg.items() if k[0] in ("correlation", "warp_correlation")]
+    levels = []
+    for (what, meta), v in sorted(corr, key=lambda kv: -corr_bytes(*kv[0][1])):
+        by = corr_bytes(*meta) + (meta[0] * meta[2] * meta[3] * 8 if what == "warp_correlation" else 0)
+        t = statistics.mean(v)
+        levels.append({"kernel": what, "B_C_H_W": list(meta), "ms": t, "algo_bytes": by, "GBps": by / (t * 1e-3) / 1e9,
+                       "gflops": 2.0 * 81 * meta[0] * meta[1] * meta[2] * meta[3] / (t * 1e-3) / 1e9})
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "corr_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = None
+    if levels:
+        top = levels[0]
+        roof = {"bound": "hbm", "kernel": f"corr_kernel<fused={top['kernel'] == 'warp_correlation'}> {top['B_C_H_W']}",
+                "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": top["GBps"] / pk["hbm_gbs"],
+                "traffic": traffic, "peak_source": pk["source"], "ms_per_launch": top["ms"],
+                "algo_bytes_per_launch": top["algo_bytes"],
+                "share_of_step": sum(statistics.mean(v) for _, v in corr) / total_kernel_ms}
+    convs = [(k, v) for k, v in agg.items() if k[0] == "conv2d"]
+    conv_ms = sum(sum(v) for _, v in convs) / nprof
+    conv_fl = sum(conv_flops(k[1]) * len(v) for k, v in convs) / nprof
+    # fp32-grade math: peak for the tensor path is the measured bf16 GEMM rate / 2 (tf32) / 3 (three passes)
+    if math == ops.MATH_FP32_SIMT:
+        cpeak, cnote = 2 * 128 * 148 * 1.965e9 / 1e12, "nominal fp32 FFMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"
+    else:
+        div = 6.0 if math == ops.MATH_TC_3XTF32 else 2.0
+        cpeak, cnote = pk["bf16_tflops_sustained"] / div, f"measured bf16 GEMM (sustained) / {div:g}"
+    roof_conv = {"bound": "tensor" if math != ops.MATH_FP32_SIMT else "fp32-simt", "achieved": conv_fl / (conv_ms * 1e-3) / 1e12,
+                 "peak": cpeak, "unit": "TFLOP/s", "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / cpeak, "peak_note": cnote,
+                 "share_of_step": conv_ms / total_kernel_ms, "flop_per_step": conv_fl, "math": math_name}
+
+    # ---- CPU baseline (bounded sample: one pair per step through the oracle on all host cores)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ts = cpu_forward_sample(args.cpu_baseline_steps, 1) if args.cpu_baseline_steps > 0 else []
+    cpu = None
+    if ts:
+        cpu = {"value": len(ts) / sum(ts), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{len(ts)} x one 1024x436 pair, oracle/irr_oracle.py (torch CPU restatement of the reference "
+                         f"forward), {sum(ts):.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "IRR_PWC full forward (7 pyramid levels, bi-directional flow + occlusion), 1024x436, "
+                               "BASELINE configs[2]", "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"batch-sharded replicas x{world} (no data-path collective)",
+                   "conv_math": math_name, "cuda_graph": graph is not None,
+                   "l2": "per-step working set (~2 GB of level-4 activations) exceeds the 126 MB L2; no explicit flush",
+                   "weights": "deterministic MSRA-like random init (no checkpoints on the box)"},
+        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * h1.numel() * 4,
+                "d2h_bytes_per_step": (oh_f.numel() + oh_o.numel()) * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": clocks,
+        "roofline": roof,
+        "roofline_corr_levels": levels[:6],
+        "roofline_conv": roof_conv,
+        "cpu_baseline": cpu,
+        "metric_reduction": {"epe_vs_synthetic_gt_mean": float(epe_all.mean()), "samples": int(epe_all.numel()),
+                             "collective": "nccl all_gather" if dist is not None else "none (1 GPU)"},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -38,6 +38,27 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# --- instrumentation used by bench.py: a launch counter, and optional per-launch CUDA-event timing on the launching
+# stream (TIMING = [] to enable; entries are (name, meta, start_event, end_event)).
+LAUNCHES = 0
+TIMING = None
+
+
+def _launch(what: str, meta, fn, *args) -> None:
+    global LAUNCHES
+    t = TIMING
+    if t is not None:
+        s = torch.cuda.Event(enable_timing=True)
+        s.record()
+    rc = fn(*args)
+    if t is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        t.append((what, meta, s, e))
+    LAUNCHES += 1
+    _lib.check(rc, what)
+
+
 def _v(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int]:
     """(data_ptr, batch_stride_in_elements) of an NCHW channel-slice view."""
     if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
@@ -77,8 +98,8 @@ def correlation(f1, f2, out=None, shift: int = 0, slope: float = 1.0, max_disp: 
         out = _new(f1, D, H, W)
     assert out.shape == (B, D, H, W)
     p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); po, so = _v(out, "out")
-    rc = _lib.load().irr_correlation_fwd(p1, s1, p2, s2, po, so, B, C, H, W, max_disp, shift, slope, _stream())
-    _lib.check(rc, "correlation")
+    _launch("correlation", (B, C, H, W), _lib.load().irr_correlation_fwd, p1, s1, p2, s2, po, so, B, C, H, W, max_disp,
+            shift, slope, _stream())
     return out
 
 
@@ -92,10 +113,9 @@ def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: floa
     lx = host_linspace(W, f1.device) if lin_x is None else lin_x
     ly = host_linspace(H, f1.device) if lin_y is None else lin_y
     p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
-    rc = _lib.load().irr_warp_correlation_fwd(p1, s1, p2, s2, pf, sf, lx.data_ptr(), ly.data_ptr(), po, so, B, C, H, W,
-                                              height_im, width_im, div_flow, max_disp, shift, slope, _grid_mode,
-                                              _stream())
-    _lib.check(rc, "warp_correlation")
+    _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd, p1, s1, p2, s2, pf, sf,
+            lx.data_ptr(), ly.data_ptr(), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp, shift, slope,
+            _grid_mode, _stream())
     return out
 
 
@@ -109,10 +129,9 @@ def warp(x, flow, height_im: int, width_im: int, div_flow: float, out=None, minu
     ly = host_linspace(H, x.device) if lin_y is None else lin_y
     px, sx = _v(x, "x"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
     pm, sm = (_v(minuend, "minuend") if minuend is not None else (None, 0))
-    rc = _lib.load().irr_warp_fwd(px, sx, pf, sf, lx.data_ptr(), ly.data_ptr(), pm, sm, po, so,
-                                  mask_out.data_ptr() if mask_out is not None else None, B, C, H, W, height_im,
-                                  width_im, div_flow, shift, _grid_mode, _stream())
-    _lib.check(rc, "warp")
+    _launch("warp", (B, C, H, W), _lib.load().irr_warp_fwd, px, sx, pf, sf, lx.data_ptr(), ly.data_ptr(), pm, sm, po, so,
+            mask_out.data_ptr() if mask_out is not None else None, B, C, H, W, height_im, width_im, div_flow, shift,
+            _grid_mode, _stream())
     return out
 
 
@@ -126,9 +145,8 @@ def correlation_generic(in1, in2, pad_size, kernel_size, max_displacement, strid
                                                      ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)),
                "correlation_generic_out_shape")
     out = torch.empty((B, oc.value, oh.value, ow.value), dtype=torch.float32, device=in1.device)
-    _lib.check(lib.irr_correlation_generic_fwd(in1.data_ptr(), in2.data_ptr(), out.data_ptr(), B, C, H, W, pad_size,
-                                               kernel_size, max_displacement, stride1, stride2, _stream()),
-               "correlation_generic")
+    _launch("correlation_generic", (B, C, H, W), lib.irr_correlation_generic_fwd, in1.data_ptr(), in2.data_ptr(),
+            out.data_ptr(), B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2, _stream())
     return out
 
 
@@ -150,8 +168,8 @@ def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
         raise RuntimeError(f"irr_b200: no packed layout for conv {Cout}x{Cin}x{ks} math={math}")
     packed = torch.empty(n // 4, dtype=torch.float32, device=w.device)
     wc = w.detach().contiguous().float()
-    _lib.check(lib.irr_conv2d_pack_weights(wc.data_ptr(), packed.data_ptr(), Cout, Cin, ks, math, _stream()),
-               "conv2d_pack_weights")
+    _launch("conv2d_pack_weights", (Cout, Cin, ks), lib.irr_conv2d_pack_weights, wc.data_ptr(), packed.data_ptr(), Cout,
+            Cin, ks, math, _stream())
     return packed
 
 
@@ -166,9 +184,9 @@ def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, s
     pa, sa = (_v(addend, "addend") if addend is not None else (None, 0))
     if addend is not None:
         assert addend.shape == out.shape
-    rc = _lib.load().irr_conv2d_fwd(px, sx, packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks,
-                                    stride, dil, slope, alpha, math, _stream())
-    _lib.check(rc, "conv2d")
+    _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), _lib.load().irr_conv2d_fwd, px, sx,
+            packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, math,
+            _stream())
     return out
 
 
@@ -177,8 +195,7 @@ def resize_ac(x, OH: int, OW: int, out=None, s_even: float = 1.0, s_odd: float =
     if out is None:
         out = _new(x, C, OH, OW)
     px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _lib.check(_lib.load().irr_resize_bilinear_ac_fwd(px, sx, po, so, B, C, H, W, OH, OW, s_even, s_odd, _stream()),
-               "resize_bilinear_ac")
+    _launch("resize_bilinear_ac", None, _lib.load().irr_resize_bilinear_ac_fwd, px, sx, po, so, B, C, H, W, OH, OW, s_even, s_odd, _stream())
     return out
 
 
@@ -187,8 +204,7 @@ def scale_channels(x, out=None, s_even: float = 1.0, s_odd: float = 1.0):
     if out is None:
         out = _new(x, C, H, W)
     px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _lib.check(_lib.load().irr_scale_channels_fwd(px, sx, po, so, B, C, H * W, s_even, s_odd, _stream()),
-               "scale_channels")
+    _launch("scale_channels", None, _lib.load().irr_scale_channels_fwd, px, sx, po, so, B, C, H * W, s_even, s_odd, _stream())
     return out
 
 
@@ -197,8 +213,7 @@ def upsample_nearest2x(x, OH: int, OW: int, out=None):
     if out is None:
         out = _new(x, C, OH, OW)
     px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _lib.check(_lib.load().irr_upsample_nearest2x_fwd(px, sx, po, so, B, C, H, W, OH, OW, _stream()),
-               "upsample_nearest2x")
+    _launch("upsample_nearest2x", None, _lib.load().irr_upsample_nearest2x_fwd, px, sx, po, so, B, C, H, W, OH, OW, _stream())
     return out
 
 
@@ -207,7 +222,7 @@ def sub_spatial_mean(x, out=None):
     if out is None:
         out = _new(x, C, H, W)
     px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _lib.check(_lib.load().irr_sub_spatial_mean_fwd(px, sx, po, so, B, C, H, W, _stream()), "sub_spatial_mean")
+    _launch("sub_spatial_mean", None, _lib.load().irr_sub_spatial_mean_fwd, px, sx, po, so, B, C, H, W, _stream())
     return out
 
 
@@ -216,7 +231,7 @@ def channel_l2norm(x, out=None):
     if out is None:
         out = _new(x, 1, H, W)
     px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _lib.check(_lib.load().irr_channel_l2norm_fwd(px, sx, po, so, B, C, H * W, _stream()), "channel_l2norm")
+    _launch("channel_l2norm", None, _lib.load().irr_channel_l2norm_fwd, px, sx, po, so, B, C, H * W, _stream())
     return out
 
 
@@ -226,5 +241,5 @@ def refine_gather(logits, src, out=None):
     if out is None:
         out = _new(src, C, H, W)
     pl, sl = _v(logits, "logits"); ps, ss = _v(src, "src"); po, so = _v(out, "out")
-    _lib.check(_lib.load().irr_refine_gather_fwd(pl, sl, ps, ss, po, so, B, C, H, W, _stream()), "refine_gather")
+    _launch("refine_gather", None, _lib.load().irr_refine_gather_fwd, pl, sl, ps, ss, po, so, B, C, H, W, _stream())
     return out
