@@ -291,16 +291,10 @@ def main():
     total_kernel_ms = sum(sum(v) for v in agg.values()) / nprof
 
     # ---- metric reduction (the only collective): per-sample EPE vs the synthetic ground truth, all-gathered
+    from irr_b200.shard import gather_metric, max_over_ranks
     epe_local = torch.norm(out["flow"] - gtc.to(dev), p=2, dim=1).mean(dim=(1, 2))
-    if dist is not None:
-        gathered = [torch.empty_like(epe_local) for _ in range(world)]
-        dist.all_gather(gathered, epe_local)
-        epe_all = torch.cat(gathered)
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-    else:
-        epe_all = epe_local
+    epe_all = gather_metric(epe_local, B * world)
+    ms, ms_e2e = max_over_ranks(ms, dev), max_over_ranks(ms_e2e, dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

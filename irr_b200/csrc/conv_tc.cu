@@ -1,15 +1,409 @@
-// tcgen05 implicit-GEMM conv path — placeholder until the kernel lands.
+// conv() of models/pwc_modules.py:8-19 as an im2col-free implicit GEMM on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+//   D[128 px x N] (fp32, TMEM) += A[128 px x K] * B[N x K]^T,   K = (channel chunk, tap) blocks of <= 32 channels.
+//
+// Why this shape:
+//   * fp32 parity (<= 1e-4, north_star) rules out a plain TF32/BF16 contraction, so the default mode is 3xTF32: every
+//     fp32 operand is split  v = hi + lo  (hi = rna_tf32(v), lo = rna_tf32(v - hi)) and the product is accumulated as
+//     hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator — 2^-21-grade products at 1/3 of the TF32 rate.
+//   * A (activations) never touches shared memory: the 8 producer warps gather the im2col row of "their" output pixel
+//     straight from NCHW global memory (lanes = consecutive pixels -> 128-byte coalesced; zero padding, stride and
+//     dilation are just address arithmetic + a predicate), split it in registers and tcgen05.st it into TMEM, where
+//     tcgen05.mma reads it as the A operand (".kind::tf32 [d], [a_tmem], b_desc").  SS-mode TF32 would saturate the
+//     128 B/clk shared-memory port with A+B operand reads; with A in TMEM only B streams through smem.
+//   * B (weights) is pre-packed on the device, once per layer, into the exact shared-memory image the MMA wants
+//     (K-major, 128-byte swizzle, hi and lo planes, one image per (N tile, K block)), so staging is one cp.async.bulk
+//     per K block completing on an mbarrier — no tensor map, no per-element work.
+//   * K order is (channel chunk outer, tap inner): the nine taps of a chunk re-read the same activation lines, which
+//     stay in L1; L2 sees each activation ~once and the weight stream once per CTA.
+//   * warp roles: warps 0-7 = A producers (two groups alternating K blocks; a warp may only touch TMEM lanes
+//     32*(warp%4)..+31, which is exactly its 32 pixels) and, at the end, the epilogue (tcgen05.ld -> bias ->
+//     LeakyReLU -> alpha/addend -> coalesced NCHW stores into the caller's channel slice); warp 8 = MMA issuer (one
+//     elected thread); warp 9 = weight loader.  Stage hand-off is mbarrier-only: a_full[s] (128 arrivals),
+//     b_full[s] (expect_tx), empty[s] (tcgen05.commit), acc_full (tcgen05.commit).
 #include "common.cuh"
+
 namespace irr {
-bool tc_supported(int, int, int, int, int) { return false; }
-size_t tc_packed_bytes(int, int, int, int) { return 0; }
-int tc_pack(const float*, void*, int, int, int, int, cudaStream_t) {
-  set_error("tcgen05 conv path not built");
-  return IRR_E_UNSUPPORTED;
+
+constexpr int TC_BM = 128;      // pixels per CTA (UMMA M)
+constexpr int TC_CK = 32;       // channels per K block (4 MMAs of K=8)
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 320;  // 8 producer/epilogue warps + MMA warp + weight-loader warp
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_ACC_COL = 0;     // accumulator columns [0, N)
+constexpr int TC_A_COL = 256;     // A stages: columns [256, 256 + 4*64)
+
+struct TcArgs {
+  const float* x; long long x_bs;
+  const uint8_t* wp;  // packed weight images
+  const float* bias;
+  const float* addend; long long a_bs;
+  float* y; long long y_bs;
+  int B, Cin, H, W, Cout, Ho, Wo, stride, dil, pad, ks;
+  int n_tile, n_tiles, cchunks, nkb, passes;
+  long long M;
+  float slope, alpha;
+};
+
+__host__ __device__ static inline int tc_round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- tile geometry shared by packer, launcher and kernel
+struct TcGeom {
+  int n_tiles, n_tile, cchunks, taps, nkb;
+  size_t img_bytes;  // one (n tile, k block) image: passes planes of n_tile x 128 B
+};
+static inline TcGeom tc_geom(int Cout, int Cin, int ks, int passes) {
+  TcGeom g;
+  g.n_tiles = (Cout + 127) / 128;
+  g.n_tile = tc_round_up((Cout + g.n_tiles - 1) / g.n_tiles, 16);
+  g.cchunks = (Cin + TC_CK - 1) / TC_CK;
+  g.taps = ks * ks;
+  g.nkb = g.cchunks * g.taps;
+  g.img_bytes = (size_t)(passes == 3 ? 2 : 1) * g.n_tile * 128;
+  return g;
 }
-int tc_conv(const float*, long long, const void*, const float*, const float*, long long, float*, long long, int, int,
-            int, int, int, int, int, int, float, float, int, cudaStream_t) {
-  set_error("tcgen05 conv path not built");
-  return IRR_E_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start
+// address >> 4 in bits [0,14), LBO (unused for swizzled K-major, set to 1) in [16,30), SBO = 1024 B >> 4 in [32,46),
+// version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int KS, int PASSES>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  constexpr int T = KS * KS;
+  constexpr int A_STAGE_COLS = PASSES == 3 ? 64 : 32;
+  const int N = p.n_tile;
+  const uint32_t plane_bytes = (uint32_t)N * 128;
+  const uint32_t img_bytes = plane_bytes * (PASSES == 3 ? 2 : 1);
+
+  // smem carve-up: [stages x image] (1024-aligned) | barriers | tmem ptr
+  uint8_t* smem_b = tc_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + (size_t)TC_STAGES * img_bytes);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto b_full = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
+  const uint32_t acc_full = bar0 + 8u * (3 * TC_STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * TC_BM;
+  const int nt = blockIdx.y;
+  const int nkb = p.nkb;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(a_full(s), 128);
+      mbar_init(b_full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 8) {
+    // ======================= A producers: gather + hi/lo split + tcgen05.st =======================
+    const int q = warp & 3, grp = warp >> 2;
+    const int row = q * 32 + lane;
+    const long long mg = m0 + row;
+    const bool m_ok = mg < p.M;
+    const int HWo = p.Ho * p.Wo;
+    int ab = 0, aoy = 0, aox = 0;
+    if (m_ok) {
+      ab = (int)(mg / HWo);
+      int rem = (int)(mg - (long long)ab * HWo);
+      aoy = rem / p.Wo;
+      aox = rem - aoy * p.Wo;
+    }
+    const int iy0 = aoy * p.stride - p.pad, ix0 = aox * p.stride - p.pad;
+    const size_t HW = (size_t)p.H * p.W;
+    const float* xb = p.x + (size_t)ab * p.x_bs;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    for (int kb = grp; kb < nkb; kb += 2) {
+      const int s = kb % TC_STAGES, it = kb / TC_STAGES;
+      const int cc = kb / T, tap = kb - cc * T;
+      const int ky = tap / KS, kx = tap - ky * KS;
+      const int iy = iy0 + ky * p.dil, ix = ix0 + kx * p.dil;
+      const bool ok = m_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+      const int c0 = cc * TC_CK;
+      const int nch = min(TC_CK, p.Cin - c0);
+      const float* src = xb + (size_t)c0 * HW + (ok ? ((size_t)iy * p.W + ix) : 0);
+      float v[TC_CK];
+#pragma unroll
+      for (int j = 0; j < TC_CK; ++j) v[j] = (ok && j < nch) ? __ldg(src + (size_t)j * HW) : 0.f;
+      mbar_wait(empty(s), (uint32_t)((it & 1) ^ 1));
+      tc_fence_after();
+      uint32_t hi[TC_CK];
+#pragma unroll
+      for (int j = 0; j < TC_CK; ++j) hi[j] = to_tf32(v[j]);
+      const uint32_t a_addr = lane_addr + (uint32_t)(TC_A_COL + s * A_STAGE_COLS);
+      tmem_st32(a_addr, hi);
+      if (PASSES == 3) {
+        uint32_t lo[TC_CK];
+#pragma unroll
+        for (int j = 0; j < TC_CK; ++j) lo[j] = to_tf32(v[j] - __uint_as_float(hi[j]));
+        tmem_st32(a_addr + 32, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(a_full(s));
+    }
+
+    // ======================= epilogue: TMEM -> bias/LeakyReLU/alpha/addend -> NCHW slice =======================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int ncols = N / 2;  // group 0: columns [0, N/2), group 1: [N/2, N)  (N is a multiple of 16 -> N/2 of 8)
+    const int col_lo = grp * ncols;
+    int bpix_b = 0, bpix = 0;
+    if (m_ok) { bpix_b = ab; bpix = (int)(mg - (long long)ab * HWo); }
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t r[16];
+      const int col = col_lo + c;
+      tmem_ld16(lane_addr + (uint32_t)(TC_ACC_COL + col), r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c + j >= ncols) break;
+          const int n = nt * N + col + j;
+          if (n < p.Cout) {
+            float val = __uint_as_float(r[j]) + __ldg(p.bias + n);
+            val = leaky(val, p.slope) * p.alpha;
+            if (p.addend) val += __ldg(p.addend + (size_t)bpix_b * p.a_bs + (size_t)n * HWo + bpix);
+            p.y[(size_t)bpix_b * p.y_bs + (size_t)n * HWo + bpix] = val;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+      // A,B K-major (bits 15,16 = 0), N>>3 in [17,23), M>>4 in [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t d_tmem = tmem_base + TC_ACC_COL;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        const int cc = kb / T;
+        const int nch = min(TC_CK, p.Cin - cc * TC_CK);
+        const int nk = (nch + 7) >> 3;
+        mbar_wait(b_full(s), ph);
+        mbar_wait(a_full(s), ph);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(smem_b + (size_t)s * img_bytes);
+        const uint64_t bd_hi = make_b_desc(b_addr);
+        const uint64_t bd_lo = make_b_desc(b_addr + plane_bytes);
+        const uint32_t a_hi = tmem_base + (uint32_t)(TC_A_COL + s * A_STAGE_COLS);
+        for (int j = 0; j < nk; ++j) {
+          const uint64_t koff = (uint64_t)((j * 32) >> 4);  // +32 bytes of K per MMA inside the 128-byte swizzled row
+          if (PASSES == 3) {
+            tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
+            tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
+            tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
+          } else {
+            tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
+          }
+        }
+        tc_commit(empty(s));
+      }
+      tc_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ======================= weight loader =======================
+    if (lane == 0) {
+      const uint8_t* wsrc = p.wp + (size_t)nt * nkb * img_bytes;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        mbar_wait(empty(s), ph ^ 1u);
+        mbar_expect_tx(b_full(s), img_bytes);
+        bulk_g2s(smem_u32(smem_b + (size_t)s * img_bytes), wsrc + (size_t)kb * img_bytes, img_bytes, b_full(s));
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packer
+// One thread per (n tile, k block, plane, row n, k j): OIHW -> swizzled K-major image (see make_b_desc).
+__global__ void pack_tc_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int ks,
+                               int n_tile, int n_tiles, int cchunks, int passes, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int T = ks * ks;
+  const int planes = passes == 3 ? 2 : 1;
+  int j = (int)(i % TC_CK);
+  long long r = i / TC_CK;
+  int n = (int)(r % n_tile); r /= n_tile;
+  int plane = (int)(r % planes); r /= planes;
+  int kb = (int)(r % (cchunks * T));
+  int nt = (int)(r / (cchunks * T));
+  int cc = kb / T, tap = kb - cc * T;
+  int c = cc * TC_CK + j, ng = nt * n_tile + n;
+  float v = 0.f;
+  if (c < Cin && ng < Cout) v = __ldg(w + ((size_t)ng * Cin + c) * T + tap);
+  uint32_t hi = to_tf32(v);
+  uint32_t val = plane == 0 ? hi : to_tf32(v - __uint_as_float(hi));
+  size_t img = (size_t)planes * n_tile * 128;
+  size_t base = ((size_t)nt * cchunks * T + kb) * img + (size_t)plane * n_tile * 128;
+  // row n: 128 bytes; 16-byte chunk (j/4) XOR (n % 8)   [Swizzle<3,4,3>]
+  size_t off = (size_t)n * 128 + (size_t)(((j >> 2) ^ (n & 7)) << 4) + (size_t)(j & 3) * 4;
+  *reinterpret_cast<uint32_t*>(out + base + off) = val;
+}
+
+bool tc_supported(int Cout, int Cin, int ks, int stride, int dil) {
+  (void)stride; (void)dil;
+  if (ks != 1 && ks != 3) return false;
+  return Cout >= 16 && Cin >= 16;  // thinner layers are not a real contraction: CUDA-core kernel
+}
+
+size_t tc_packed_bytes(int Cout, int Cin, int ks, int math) {
+  int passes = math == IRR_MATH_TC_3XTF32 ? 3 : 1;
+  TcGeom g = tc_geom(Cout, Cin, ks, passes);
+  return (size_t)g.n_tiles * g.nkb * g.img_bytes;
+}
+
+int tc_pack(const float* w, void* out, int Cout, int Cin, int ks, int math, cudaStream_t st) {
+  int passes = math == IRR_MATH_TC_3XTF32 ? 3 : 1;
+  TcGeom g = tc_geom(Cout, Cin, ks, passes);
+  long long total = (long long)g.n_tiles * g.nkb * (passes == 3 ? 2 : 1) * g.n_tile * TC_CK;
+  pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, (uint8_t*)out, Cout, Cin, ks, g.n_tile, g.n_tiles,
+                                                                  g.cchunks, passes, total);
+  return check_launch("irr_conv2d_pack_weights");
+}
+
+template <int KS, int PASSES>
+static int launch_tc(const TcArgs& a, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_smem = smem;
+  }
+  dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), a.n_tiles);
+  conv_tc_kernel<KS, PASSES><<<grid, TC_THREADS, smem, st>>>(a);
+  return check_launch("irr_conv2d_fwd");
+}
+
+int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
+            float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
+            float alpha, int math, cudaStream_t st) {
+  int passes = math == IRR_MATH_TC_3XTF32 ? 3 : 1;
+  TcGeom g = tc_geom(Cout, Cin, ks, passes);
+  TcArgs a;
+  a.x = x; a.x_bs = x_bs; a.wp = (const uint8_t*)w; a.bias = bias; a.addend = addend; a.a_bs = a_bs; a.y = y; a.y_bs = y_bs;
+  a.B = B; a.Cin = Cin; a.H = H; a.W = W; a.Cout = Cout; a.stride = stride; a.dil = dil; a.ks = ks;
+  a.pad = ((ks - 1) * dil) / 2;
+  a.Ho = (H + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
+  a.Wo = (W + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
+  a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb; a.passes = passes;
+  a.M = (long long)B * a.Ho * a.Wo;
+  a.slope = slope; a.alpha = alpha;
+  size_t smem = (size_t)TC_STAGES * g.img_bytes + (3 * TC_STAGES + 1) * 8 + 16;
+  if (ks == 1) return passes == 3 ? launch_tc<1, 3>(a, smem, st) : launch_tc<1, 1>(a, smem, st);
+  return passes == 3 ? launch_tc<3, 3>(a, smem, st) : launch_tc<3, 1>(a, smem, st);
+}
+
 }  // namespace irr

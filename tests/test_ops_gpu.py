@@ -240,3 +240,51 @@ def test_refine_pieces(cuda):
     logits = torch.from_numpy(rs(63, (2, 9, 14, 22))) * 2
     ref = O._kernel_gather(fl, logits)
     assert (ops.refine_gather(logits.to(cuda), fl.to(cuda)).cpu() - ref).abs().max().item() <= 1e-5
+
+
+# ------------------------------------------------------------------ tcgen05 conv path
+TC_CASES = [
+    # (B, Cin, H, W, Cout, k, stride, dil)
+    (1, 32, 16, 32, 32, 1, 1, 1),      # smallest: one K block, N = 32
+    (1, 32, 16, 32, 32, 3, 1, 1),
+    (2, 115, 28, 64, 128, 3, 1, 1),    # dense block conv1 (ragged channel tail 115 = 3*32 + 19)
+    (1, 565, 14, 32, 128, 3, 1, 1),    # context conv0
+    (1, 128, 28, 64, 96, 3, 1, 8), (1, 96, 28, 64, 64, 3, 1, 16),
+    (2, 16, 47, 78, 32, 3, 2, 1),      # feature-extractor style stride 2, odd sizes
+    (1, 128, 14, 32, 196, 3, 2, 1),    # two N tiles (196 -> 2 x 112)
+    (2, 196, 7, 16, 32, 1, 1, 1), (1, 35, 13, 39, 128, 3, 1, 1), (1, 243, 24, 39, 128, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+def test_conv2d_tcgen05_vs_torch_cpu(cuda, case, mode):
+    from irr_b200 import ops
+    B, Cin, H, W, Cout, k, s, d = case
+    math = ops.MATH_TC_3XTF32 if mode == "3xtf32" else ops.MATH_TC_TF32
+    assert ops.tc_supported(Cout, Cin, k, s, d)
+    x = torch.from_numpy(rs(41, (B, Cin, H, W)))
+    w = torch.from_numpy(rs(42, (Cout, Cin, k, k))) * float(np.sqrt(2.0 / (Cin * k * k)))
+    b = torch.from_numpy(rs(43, (Cout,))) * 0.1
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s, padding=((k - 1) * d) // 2, dilation=d), 0.1)
+    packed = ops.pack_weights(w.to(cuda), math)
+    got = ops.conv2d(x.to(cuda), packed, b.to(cuda), Cout, k, s, d, slope=0.1, math=math)
+    err = (got.cpu().double() - ref).abs().max().item()
+    print(f"[tc] {case} {mode}: max-abs {err:.3e}")
+    assert err <= (1e-4 if mode == "3xtf32" else 2e-2)
+
+
+def test_conv2d_tcgen05_slices_addend(cuda):
+    from irr_b200 import ops
+    B, Ct, H, W = 2, 100, 20, 36
+    buf = torch.from_numpy(rs(51, (B, Ct, H, W))).to(cuda)
+    w = torch.from_numpy(rs(52, (48, 72, 3, 3))) * 0.05
+    b = torch.from_numpy(rs(53, (48,))) * 0.1
+    add = torch.from_numpy(rs(54, (B, 48, H, W))).to(cuda)
+    ref = add.cpu() + 0.1 * torch.nn.functional.conv2d(buf[:, 28:100].cpu(), w, b, padding=1)
+    out = torch.zeros((B, 60, H, W), device=cuda)
+    ops.conv2d(buf[:, 28:100], ops.pack_weights(w.to(cuda), ops.MATH_TC_3XTF32), b.to(cuda), 48, 3, slope=1.0,
+               out=out[:, 5:53], addend=add, alpha=0.1, math=ops.MATH_TC_3XTF32)
+    assert (out[:, 5:53].cpu() - ref).abs().max().item() <= 1e-4
+    assert (out[:, :5] == 0).all() and (out[:, 53:] == 0).all()
