@@ -108,6 +108,13 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_threads():
+    """Host threads for the CPU reference arm.  The forward is ~16 k small ATen ops: beyond ~16 threads the
+    per-op fork/join cost grows faster than the work shrinks (measured on the 128-core box: 45 s/pair with 128 threads vs
+    ~2.5 s/pair with 8 in the build container), so the arm uses min(cores, 16) and reports that count."""
+    return max(1, min(os.cpu_count() or 1, env_int("IRR_CPU_THREADS", 16)))
+
+
 def corr_bytes(B, C, H, W):  # SURVEY.md §8(d): B*H*W*(2*C*4 + 81*4); fused warp adds the flow read B*H*W*8
     return B * H * W * (8 * C + 324)
 
@@ -122,8 +129,7 @@ def cpu_forward_sample(steps, warmup, threads=None):
     """Times the oracle (CPU restatement of the reference forward; oracle/irr_oracle.py) on a bounded sample:
     one 1024x436 pair per step."""
     from oracle import irr_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or cpu_threads())
     p = O.synthetic_params("IRR_PWC", seed=1234, gain=0.7)
     i1, i2, _ = O.synthetic_pair(1, H_IM, W_IM, seed=3, max_flow=20.0)
     ts = []
@@ -141,8 +147,6 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 1))
     ts = cpu_forward_sample(steps, warm)
@@ -174,7 +178,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--math", default=os.environ.get("IRR_MATH", "auto"), choices=["auto", "fp32", "3xtf32", "tf32"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--cpu-baseline-steps", type=int, default=4)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -340,8 +344,6 @@ def main():
                  "share_of_step": conv_ms / total_kernel_ms, "flop_per_step": conv_fl, "math": math_name}
 
     # ---- CPU baseline (bounded sample: one pair per step through the oracle on all host cores)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     ts = cpu_forward_sample(args.cpu_baseline_steps, 1) if args.cpu_baseline_steps > 0 else []
     cpu = None
     if ts:

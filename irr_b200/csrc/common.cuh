@@ -23,6 +23,31 @@ static inline cudaStream_t as_stream(irr_stream_t s) { return reinterpret_cast<c
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // ---------------------------------------------------------------------------------------------------------
+// mbarrier / shared-address helpers (producer-consumer pipelines inside one CTA)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Sampling-grid arithmetic of WarpingLayer (models/pwc_modules.py:119-127) + grid_sampler_2d's unnormalise
 // (ATen/native/cuda/GridSampler.cuh:22-31).  Every op is an explicitly rounded intrinsic so ptxas cannot
 // contract or reassociate: the validity mask `sum_w >= 1.0f` (pwc_modules.py:131) is bit-sensitive.

@@ -4,18 +4,23 @@
 // models/correlation_package/correlation_cuda_kernel.cu:41-114:  out[b, (dy+4)*9+(dx+4), y, x] =
 // (1/C) sum_c f1[b,c,y,x] * f2w[b,c,y+dy,x+dx], zero outside the image.
 //
-// B200 design (HBM-bound op sitting at the fp32-FMA ridge):
-//   * one CTA = one 8 x 32 output tile of one image, 9 warps; warp w owns displacement row dy = w-4, lane = (row r of
-//     the tile, 8-pixel strip s).  Each thread keeps 8 px x 9 dx = 72 fp32 accumulators, so one channel step is
-//     2 + 4 LDS.128 for 72 FFMA — the register tile that keeps the FMA pipe, not the LSU, the limiter.
-//   * operands are staged per 8-channel chunk in shared memory: f1 tile [8][8][36], f2 halo tile [8][16][44].  The row
-//     pitches 36 / 44 (== 4, 12 mod 32 words) make every quarter-warp LDS.128 (8 rows, same strip) hit 32 distinct
-//     banks.  Global reads are coalesced along W; f2's 2.5x halo re-read is served by the 126 MB L2 (the largest
-//     level-4 map of cfg 3 is 28.6 MB), so DRAM traffic stays at the algorithmic B*H*W*(8C+324) bytes.
-//   * in the fused-warp variant the f2 halo tile is produced by a 4-tap gather straight into shared memory; the
-//     sample coordinates / weights / mask of the 16 x 40 halo pixels are computed once per tile (bit-exact recipe in
-//     common.cuh) and reused for every channel.  The warped tensor never exists in HBM.
-//   * epilogue: * 1/C, LeakyReLU, 16-byte stores into the caller's channel slice of the estimator input buffer.
+// B200 design (HBM-bound op sitting at the fp32-FMA ridge) — persistent, warp-specialised:
+//   * grid = min(#tiles, #SMs) persistent CTAs of 16 warps; each CTA walks 8 x 32 output tiles of the (2B) batch.
+//   * warps 0-8 = COMPUTE: warp w owns displacement row dy = w-4, lane = (tile row r, 8-pixel strip s); 8 px x 9 dx = 72
+//     fp32 accumulators per thread, so one channel step is 2 + 4 LDS.128 for 72 FFMA — the register tile that keeps
+//     the FMA pipe, not the LSU, the limiter (the reference kernel does 1 FMA per 2 global loads and re-reads f1 81x).
+//   * warps 9-15 = PRODUCERS: they stage 8-channel chunks of the f1 tile [8][8][36] and the f2 halo tile [8][16][44]
+//     into a 3-stage shared-memory ring (mbarrier full/empty), running ahead of the compute warps — across tile
+//     boundaries too, so the epilogue of tile t overlaps the loads of tile t+1.  Each producer thread owns <= 3 fixed
+//     halo positions: in the fused-warp variant it computes the sample coordinates / bilinear weights / hard mask of
+//     those positions ONCE per tile (bit-exact recipe in common.cuh), keeps them in registers and issues the 4-tap
+//     gathers of all 8 channels of a chunk back to back (32 independent loads in flight per thread).  The warped
+//     tensor never exists in HBM.
+//   * row pitches 36 / 44 words (== 4, 12 mod 32) make every quarter-warp LDS.128 (8 rows, same strip) conflict-free.
+//   * global reads are coalesced along W; f2's 2.5x halo re-read is served by the 126 MB L2 (the largest level-4 map
+//     of cfg 3 is 28.6 MB), so DRAM traffic stays at the algorithmic B*H*W*(8C+324) bytes.
+//   * epilogue: / C, LeakyReLU, 16-byte stores into the caller's channel slice of the estimator input buffer.
+// No tensor cores by design (a 9x9-window dot product, not a GEMM).
 #include "common.cuh"
 
 namespace irr {
@@ -26,149 +31,230 @@ constexpr int F2_H = TH + 2 * MD;           // 16
 constexpr int F2_WV = TW + 2 * MD;          // 40 valid halo columns
 constexpr int F2_P = 44;                    // f2 row pitch (floats)
 constexpr int CC = 8;                       // channels per chunk
-constexpr int CORR_THREADS = 32 * ND;       // 288
+constexpr int NCOMP = 32 * ND;              // 288 compute threads
+constexpr int NPROD = 224;                  // 7 producer warps
+constexpr int CORR_THREADS = NCOMP + NPROD; // 512
+constexpr int CORR_STAGES = 3;
 constexpr int F1_ELEMS = CC * TH * F1_P;    // 2304
 constexpr int F2_ELEMS = CC * F2_H * F2_P;  // 5632
+constexpr int STAGE_ELEMS = F1_ELEMS + F2_ELEMS;
 constexpr int NHALO = F2_H * F2_WV;         // 640
+constexpr int NF1 = TH * TW;                // 256
+constexpr int CORR_SMEM = CORR_STAGES * STAGE_ELEMS * 4 + 2 * CORR_STAGES * 8;
 
-struct HaloTap {  // 24 bytes per halo pixel (fused-warp variant)
-  int off;        // clamped (y0*W + x0)
-  int dxy;        // bit0: x1 = x0+1 is a distinct in-range column; bit1: same for y
-  float w00, w01, w10, w11;  // mask already folded in
+struct ProdPos {  // one halo (or f1) position owned by a producer thread
+  int soff;       // offset inside the stage for channel 0 (floats); < 0 => unused slot
+  int goff;       // global offset (y*W + x), clamped; for fused: clamped (y0*W + x0)
+  int dx, dy;     // fused: +1 / +W when the second column / row is a distinct in-range texel, else 0
+  float w00, w01, w10, w11;  // fused: bilinear weights with mask and bounds folded in; plain: w00 = 1 if in image else 0
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(CORR_THREADS, 2)
+__global__ void __launch_bounds__(CORR_THREADS, 1)
     corr_kernel(const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                 const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
-                GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok) {
+                GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
+                int ntiles) {
   extern __shared__ __align__(16) float smem[];
-  float* f1s = smem;
-  float* f2s = smem + F1_ELEMS;
-  HaloTap* taps = reinterpret_cast<HaloTap*>(smem + F1_ELEMS + F2_ELEMS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CORR_STAGES * STAGE_ELEMS);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (CORR_STAGES + s); };
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.z;
-  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
   const int HW = H * W;
-  int b2 = b + shift;
-  if (b2 >= B) b2 -= B;
-  const float* f1b = f1 + (size_t)b * f1_bs;
-  const float* f2b = f2 + (size_t)b2 * f2_bs;
-
-  if (FUSED) {
-    const float* fl = flow + (size_t)b * flow_bs;
-    for (int i = tid; i < NHALO; i += CORR_THREADS) {
-      int hr = i / F2_WV, hx = i - hr * F2_WV;
-      int gy = y0 - MD + hr, gx = x0 - MD + hx;
-      HaloTap t;
-      t.off = 0; t.dxy = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        float u = __ldg(fl + (size_t)gy * W + gx), v = __ldg(fl + HW + (size_t)gy * W + gx);
-        float ix, iy;
-        sample_coords(g, u, v, gx, gy, W, H, ix, iy);
-        Taps tp = make_taps(ix, iy, W, H);
-        if (tp.mask != 0.f) {
-          int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
-          int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
-          t.off = ya * W + xa;
-          t.dxy = (xb != xa ? 1 : 0) | (yb != ya ? 2 : 0);
-          // a clamped (out-of-range) tap has zero weight (make_taps), so aliasing it onto its in-range
-          // neighbour's address is harmless: the four reads below are always in bounds.
-          t.w00 = tp.w00; t.w01 = tp.w01; t.w10 = tp.w10; t.w11 = tp.w11;
-        }
-      }
-      taps[i] = t;
+  const int nchunks = (C + CC - 1) / CC;
+  if (tid == 0) {
+    for (int s = 0; s < CORR_STAGES; ++s) {
+      mbar_init(full(s), NPROD / 32);   // one elected arrival per producer warp
+      mbar_init(empty(s), NCOMP / 32);  // one elected arrival per compute warp
     }
-    __syncthreads();
+    mbar_fence_init();
   }
+  __syncthreads();
 
-  const int dyi = tid >> 5;  // 0..8  -> dy = dyi - 4
-  const int lane = tid & 31;
-  const int r = lane & 7, s = lane >> 3;
-
-  float acc[ND][PX];
+  if (tid >= NCOMP) {
+    // ============================== PRODUCERS ==============================
+    const int pt = tid - NCOMP;
+    const int lane = tid & 31;
+    int gchunk = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int y0 = ty * TH, x0 = tx * TW;
+      int b2 = b + shift;
+      if (b2 >= B) b2 -= B;
+      const float* f1b = f1 + (size_t)b * f1_bs;
+      const float* f2b = f2 + (size_t)b2 * f2_bs;
+      // ---- positions owned by this thread: up to 3 f2 halo slots + up to 2 f1 slots (balanced: 3+1 or 2+2)
+      ProdPos hp[3];
 #pragma unroll
-  for (int d = 0; d < ND; ++d)
-#pragma unroll
-    for (int p = 0; p < PX; ++p) acc[d][p] = 0.f;
-
-  for (int c0 = 0; c0 < C; c0 += CC) {
-    // ---- stage f1 chunk: [CC][TH][TW], coalesced along x
-    for (int i = tid; i < CC * TH * TW; i += CORR_THREADS) {
-      int xx = i & (TW - 1);
-      int rr = (i >> 5) & (TH - 1);
-      int cc = i >> 8;
-      int gy = y0 + rr, gx = x0 + xx, c = c0 + cc;
-      float v = 0.f;
-      if (c < C && gy < H && gx < W) v = __ldg(f1b + (size_t)c * HW + (size_t)gy * W + gx);
-      f1s[(cc * TH + rr) * F1_P + xx] = v;
-    }
-    // ---- stage f2 halo chunk: [CC][16][40]
-    for (int i = tid; i < CC * NHALO; i += CORR_THREADS) {
-      int cc = i / NHALO;
-      int h = i - cc * NHALO;
-      int hr = h / F2_WV, hx = h - hr * F2_WV;
-      int c = c0 + cc;
-      float v = 0.f;
-      if (FUSED) {
-        if (c < C) {
-          HaloTap t = taps[h];
-          const float* p = f2b + (size_t)c * HW + t.off;
-          int dx = t.dxy & 1, dy = (t.dxy & 2) ? W : 0;
-          float a = __fmul_rn(__ldg(p), t.w00);
-          a = fmaf(__ldg(p + dx), t.w01, a);
-          a = fmaf(__ldg(p + dy), t.w10, a);
-          a = fmaf(__ldg(p + dy + dx), t.w11, a);
-          v = a;
+      for (int k = 0; k < 3; ++k) {
+        const int h = pt + k * NPROD;
+        ProdPos q;
+        q.soff = -1; q.goff = 0; q.dx = 0; q.dy = 0; q.w00 = q.w01 = q.w10 = q.w11 = 0.f;
+        if (h < NHALO) {
+          const int hr = h / F2_WV, hx = h - hr * F2_WV;
+          const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+          q.soff = F1_ELEMS + hr * F2_P + hx;
+          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            if (FUSED) {
+              const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * W + gx;
+              float ix, iy;
+              sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
+              Taps tp = make_taps(ix, iy, W, H);
+              if (tp.mask != 0.f) {
+                const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
+                const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
+                q.goff = ya * W + xa;
+                q.dx = (xb != xa) ? 1 : 0;
+                q.dy = (yb != ya) ? W : 0;
+                // a clamped (out-of-range) tap has zero weight (make_taps), so aliasing it onto its in-range
+                // neighbour's address is harmless: the four reads are always in bounds.
+                q.w00 = tp.w00; q.w01 = tp.w01; q.w10 = tp.w10; q.w11 = tp.w11;
+              }
+            } else {
+              q.goff = gy * W + gx;
+              q.w00 = 1.f;
+            }
+          }
         }
-      } else {
-        int gy = y0 - MD + hr, gx = x0 - MD + hx;
-        if (c < C && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(f2b + (size_t)c * HW + (size_t)gy * W + gx);
+        hp[k] = q;
       }
-      f2s[(cc * F2_H + hr) * F2_P + hx] = v;
-    }
-    __syncthreads();
-    // ---- 8 channels x (8 px x 9 dx) FFMA per thread
-#pragma unroll 2
-    for (int cc = 0; cc < CC; ++cc) {
-      const float4* ap = reinterpret_cast<const float4*>(f1s + (cc * TH + r) * F1_P + s * PX);
-      const float4* bp = reinterpret_cast<const float4*>(f2s + (cc * F2_H + r + dyi) * F2_P + s * PX);
-      float a[PX], bv[PX + 2 * MD];
-      float4 t0 = ap[0], t1 = ap[1];
-      a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+      int f1s_off[2], f1g_off[2];
+      float f1ok[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 t = bp[q];
-        bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+      for (int k = 0; k < 2; ++k) {
+        int q = (k == 0) ? pt : (pt >= 192 ? NPROD + (pt - 192) : -1);
+        f1s_off[k] = -1; f1g_off[k] = 0; f1ok[k] = 0.f;
+        if (q >= 0 && q < NF1) {
+          const int rr = q >> 5, xx = q & 31;
+          const int gy = y0 + rr, gx = x0 + xx;
+          f1s_off[k] = rr * F1_P + xx;
+          if (gy < H && gx < W) { f1g_off[k] = gy * W + gx; f1ok[k] = 1.f; }
+        }
       }
+      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+        const int s = gchunk % CORR_STAGES;
+        const uint32_t ph = (uint32_t)((gchunk / CORR_STAGES) & 1);
+        const int c0 = ci * CC;
+        mbar_wait(empty(s), ph ^ 1u);
+        float* st = smem + s * STAGE_ELEMS;
+        // f2 halo: 8 channels of each owned position, loads issued back to back
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (hp[k].soff >= 0) {
+            float v[CC];
+            if (FUSED) {
+              const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
+              float t00[CC], t01[CC], t10[CC], t11[CC];
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) {
+                const bool okc = (c0 + cc < C) && (hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f);
+                const float* pc = p + (size_t)cc * HW;
+                t00[cc] = okc ? __ldg(pc) : 0.f;
+                t01[cc] = okc ? __ldg(pc + hp[k].dx) : 0.f;
+                t10[cc] = okc ? __ldg(pc + hp[k].dy) : 0.f;
+                t11[cc] = okc ? __ldg(pc + hp[k].dy + hp[k].dx) : 0.f;
+              }
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) {
+                float a = __fmul_rn(t00[cc], hp[k].w00);  // tap order of grid_sampler_2d
+                a = fmaf(t01[cc], hp[k].w01, a);
+                a = fmaf(t10[cc], hp[k].w10, a);
+                v[cc] = fmaf(t11[cc], hp[k].w11, a);
+              }
+            } else {
+              const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc)
+                v[cc] = (hp[k].w00 != 0.f && c0 + cc < C) ? __ldg(p + (size_t)cc * HW) : 0.f;
+            }
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) st[hp[k].soff + cc * (F2_H * F2_P)] = v[cc];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (f1s_off[k] >= 0) {
+            const float* p = f1b + (size_t)c0 * HW + f1g_off[k];
+            float v[CC];
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) v[cc] = (f1ok[k] != 0.f && c0 + cc < C) ? __ldg(p + (size_t)cc * HW) : 0.f;
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) st[f1s_off[k] + cc * (TH * F1_P)] = v[cc];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full(s));
+      }
+    }
+  } else {
+    // ============================== COMPUTE ==============================
+    const int dyi = tid >> 5;  // 0..8  -> dy = dyi - 4
+    const int lane = tid & 31;
+    const int r = lane & 7, s8 = lane >> 3;
+    int gchunk = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int y0 = ty * TH, x0 = tx * TW;
+      float acc[ND][PX];
 #pragma unroll
       for (int d = 0; d < ND; ++d)
 #pragma unroll
-        for (int p = 0; p < PX; ++p) acc[d][p] = fmaf(a[p], bv[p + d], acc[d][p]);
-    }
-    __syncthreads();
-  }
+        for (int p = 0; p < PX; ++p) acc[d][p] = 0.f;
 
-  // ---- epilogue: mean over channels (pwc_modules.py:59 / .cu:107 divide by nelems), LeakyReLU (IRR_PWC.py:94-95)
-  const int gy = y0 + r;
-  const int gx = x0 + s * PX;
-  if (gy < H && gx < W) {
-    const float fc = (float)C;
-    float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
+      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+        const int s = gchunk % CORR_STAGES;
+        const uint32_t ph = (uint32_t)((gchunk / CORR_STAGES) & 1);
+        mbar_wait(full(s), ph);
+        const float* f1s = smem + s * STAGE_ELEMS;
+        const float* f2s = f1s + F1_ELEMS;
+#pragma unroll 2
+        for (int cc = 0; cc < CC; ++cc) {
+          const float4* ap = reinterpret_cast<const float4*>(f1s + (cc * TH + r) * F1_P + s8 * PX);
+          const float4* bp = reinterpret_cast<const float4*>(f2s + (cc * F2_H + r + dyi) * F2_P + s8 * PX);
+          float a[PX], bv[PX + 2 * MD];
+          float4 t0 = ap[0], t1 = ap[1];
+          a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      float v[PX];
+          for (int q = 0; q < 4; ++q) {
+            float4 t = bp[q];
+            bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+          }
 #pragma unroll
-      for (int p = 0; p < PX; ++p) v[p] = leaky(__fdiv_rn(acc[d][p], fc), slope);
-      float* q = op + (size_t)d * HW;
-      if (vec_ok && gx + PX <= W) {
-        reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4*>(q)[1] = make_float4(v[4], v[5], v[6], v[7]);
-      } else {
+          for (int d = 0; d < ND; ++d)
 #pragma unroll
-        for (int p = 0; p < PX; ++p)
-          if (gx + p < W) q[p] = v[p];
+            for (int p = 0; p < PX; ++p) acc[d][p] = fmaf(a[p], bv[p + d], acc[d][p]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty(s));
+      }
+
+      // ---- epilogue: mean over channels (pwc_modules.py:59 / .cu:107 divide by nelems), LeakyReLU (IRR_PWC.py:94-95)
+      const int gy = y0 + r;
+      const int gx = x0 + s8 * PX;
+      if (gy < H && gx < W) {
+        const float fc = (float)C;
+        float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          float v[PX];
+#pragma unroll
+          for (int p = 0; p < PX; ++p) v[p] = leaky(__fdiv_rn(acc[d][p], fc), slope);
+          float* q = op + (size_t)d * HW;
+          if (vec_ok && gx + PX <= W) {
+            reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(q)[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+              if (gx + p < W) q[p] = v[p];
+          }
+        }
       }
     }
   }
@@ -209,10 +295,9 @@ template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
                        int C, int H, int W, int shift, float slope, cudaStream_t st) {
-  size_t smem = (size_t)(F1_ELEMS + F2_ELEMS) * sizeof(float) + (FUSED ? NHALO * sizeof(HaloTap) : 0);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(corr_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(corr_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
       return (int)e;
@@ -220,9 +305,13 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
     attr_done = true;
   }
   int vec_ok = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
-  corr_kernel<FUSED><<<grid, CORR_THREADS, smem, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
-                                                       shift, slope, vec_ok);
+  int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  long long nt = (long long)tiles_x * tiles_y * B;
+  if (nt > 0x7fffffffLL) return fail_arg(fn, "too many tiles");
+  int ntiles = (int)nt;
+  int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
+  corr_kernel<FUSED><<<grid, CORR_THREADS, CORR_SMEM, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H,
+                                                            W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles);
   return check_launch(fn);
 }
 
@@ -238,7 +327,6 @@ int irr_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long 
   const char* fn = "irr_correlation_fwd";
   IRR_REQUIRE(f1 && f2 && out, fn, "null pointer");
   IRR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, fn, "non-positive size");
-  IRR_REQUIRE(B <= 65535 && (H + TH - 1) / TH <= 65535, fn, "size exceeds grid limits");
   IRR_REQUIRE(max_disp == MD, fn, "only max_disp == 4 is compiled (use irr_correlation_generic_fwd)");
   IRR_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < B, fn, "f2_batch_shift out of range");
   GridArgs g = make_grid_args(nullptr, nullptr, H, W, H, W, 1.f, 0);
@@ -253,7 +341,6 @@ int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, 
   const char* fn = "irr_warp_correlation_fwd";
   IRR_REQUIRE(f1 && f2 && flow && out, fn, "null pointer");
   IRR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && H_im > 0 && W_im > 0, fn, "non-positive size");
-  IRR_REQUIRE(B <= 65535 && (H + TH - 1) / TH <= 65535, fn, "size exceeds grid limits");
   IRR_REQUIRE(max_disp == MD, fn, "only max_disp == 4 is compiled");
   IRR_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < B, fn, "f2_batch_shift out of range");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
