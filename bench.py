@@ -293,6 +293,11 @@ def main():
     for what, meta, s, e in timing:
         agg.setdefault((what, meta), []).append(s.elapsed_time(e))
     total_kernel_ms = sum(sum(v) for v in agg.values()) / nprof
+    if rank == 0 and os.environ.get("IRR_DUMP_TIMES"):
+        rows = [{"kernel": k[0], "meta": list(k[1]) if k[1] is not None else None, "launches_per_step": len(v) / nprof,
+                 "ms_per_step": sum(v) / nprof, "mean_us": 1e3 * sum(v) / len(v)} for k, v in agg.items()]
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        json.dump(rows, open(os.environ["IRR_DUMP_TIMES"], "w"), indent=0)
 
     # ---- metric reduction (the only collective): per-sample EPE vs the synthetic ground truth, all-gathered
     from irr_b200.shard import gather_metric, max_over_ranks
