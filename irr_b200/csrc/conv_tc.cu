@@ -27,8 +27,6 @@ namespace irr {
 
 constexpr int TC_BM = 128;      // pixels per CTA (UMMA M)
 constexpr int TC_CK = 32;       // channels per K block (4 MMAs of K=8)
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 320;  // 8 producer/epilogue warps + MMA warp + weight-loader warp
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_ACC_COL = 0;     // accumulator columns [0, N)
 constexpr int TC_A_COL = 256;     // A stages: columns [256, 256 + 4*64)
@@ -40,7 +38,8 @@ struct TcArgs {
   const float* addend; long long a_bs;
   float* y; long long y_bs;
   int B, Cin, H, W, Cout, Ho, Wo, stride, dil, pad, ks;
-  int n_tile, n_tiles, cchunks, nkb, passes;
+  int n_tile, n_tiles, cchunks, nkb, passes, resident;
+  unsigned b_smem_bytes;
   long long M;
   float slope, alpha;
 };
@@ -124,38 +123,71 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+// Persistent: grid = #SMs; each CTA walks (n tile, 256-pixel M tile) work items.  One work item = two 128-row halves
+// that share every weight stage (halves the weight stream per pixel) and own one TMEM accumulator each.
+//   warps 0-3 : A producers, half 0      warps 4-7 : A producers, half 1
+//   warp 8    : MMA issuer (lane 0)      warp 9    : weight loader (lane 0)
+//   warps 12-15: epilogue (TMEM lane quadrant = warp % 4)
+// TMEM columns: [0,256) accumulators (2 halves x N, double-buffered across work items when N <= 64),
+//               [256,512) A ring: stage = 2 halves x (hi 32 | lo 32) columns -> 2 stages (3xTF32) / 4 stages (TF32).
+// Weights: resident in shared memory for the whole kernel when the layer's images fit (K <= ~9 blocks at N=128, every
+// N=32 layer), otherwise a 4-stage cp.async.bulk ring.
+constexpr int TC_BM2 = 256;
+constexpr int TC_THREADS2 = 512;
+constexpr int TC_SB = 4;                   // weight ring depth (streaming mode)
+constexpr size_t TC_RESIDENT_MAX = 168 * 1024;
+
+struct TcSeq {  // flat (work item, k block) iterator shared by all roles
+  int item, kb, nkb, items, stride;
+  __device__ __forceinline__ bool valid() const { return item < items; }
+  __device__ __forceinline__ void next() {
+    if (++kb == nkb) { kb = 0; item += stride; }
+  }
+};
+
 template <int KS, int PASSES>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p) {
+__global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   constexpr int T = KS * KS;
-  constexpr int A_STAGE_COLS = PASSES == 3 ? 64 : 32;
+  constexpr int A_COLS = PASSES == 3 ? 64 : 32;       // per half per stage
+  constexpr int SA = 256 / (2 * A_COLS);              // 2 or 4
   const int N = p.n_tile;
+  const int NBUF = N <= 64 ? 2 : 1;
+  const int acc_stride = N <= 64 ? 64 : 128;
   const uint32_t plane_bytes = (uint32_t)N * 128;
   const uint32_t img_bytes = plane_bytes * (PASSES == 3 ? 2 : 1);
+  const int nkb = p.nkb;
+  const bool resident = p.resident != 0;
+  const int m_tiles = (int)((p.M + TC_BM2 - 1) / TC_BM2);
+  const int items = m_tiles * p.n_tiles;
 
-  // smem carve-up: [stages x image] (1024-aligned) | barriers | tmem ptr
   uint8_t* smem_b = tc_smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + (size_t)TC_STAGES * img_bytes);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + p.b_smem_bytes);
+  // barrier map
   const uint32_t bar0 = smem_u32(bars);
-  auto a_full = [&](int s) { return bar0 + 8u * s; };
-  auto b_full = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-  auto empty = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
-  const uint32_t acc_full = bar0 + 8u * (3 * TC_STAGES);
+  auto a_full = [&](int s, int h) { return bar0 + 8u * (s * 2 + h); };            // [0, 8)
+  auto a_empty = [&](int s) { return bar0 + 8u * (8 + s); };                      // [8, 12)
+  auto b_full = [&](int s) { return bar0 + 8u * (12 + s); };                      // [12, 16)
+  auto b_empty = [&](int s) { return bar0 + 8u * (16 + s); };                     // [16, 20)
+  auto acc_full = [&](int b) { return bar0 + 8u * (20 + b); };                    // [20, 22)
+  auto acc_empty = [&](int b) { return bar0 + 8u * (22 + b); };                   // [22, 24)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long m0 = (long long)blockIdx.x * TC_BM;
-  const int nt = blockIdx.y;
-  const int nkb = p.nkb;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(a_full(s), 128);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(a_full(s, 0), 4);
+      mbar_init(a_full(s, 1), 4);
+      mbar_init(a_empty(s), 1);
       mbar_init(b_full(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(b_empty(s), 1);
     }
-    mbar_init(acc_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 4);
+    }
+    mbar_fence_init();
   }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
@@ -167,44 +199,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int HWo = p.Ho * p.Wo;
+
+  TcSeq seq;
+  seq.item = blockIdx.x; seq.kb = 0; seq.nkb = nkb; seq.items = items; seq.stride = gridDim.x;
 
   if (warp < 8) {
-    // ======================= A producers: gather + hi/lo split + tcgen05.st =======================
-    const int q = warp & 3, grp = warp >> 2;
-    const int row = q * 32 + lane;
-    const long long mg = m0 + row;
-    const bool m_ok = mg < p.M;
-    const int HWo = p.Ho * p.Wo;
-    int ab = 0, aoy = 0, aox = 0;
-    if (m_ok) {
-      ab = (int)(mg / HWo);
-      int rem = (int)(mg - (long long)ab * HWo);
-      aoy = rem / p.Wo;
-      aox = rem - aoy * p.Wo;
-    }
-    const int iy0 = aoy * p.stride - p.pad, ix0 = aox * p.stride - p.pad;
+    // ======================= A producers =======================
+    const int h = warp >> 2, q = warp & 3;
+    const int row = h * 128 + q * 32 + lane;
     const size_t HW = (size_t)p.H * p.W;
-    const float* xb = p.x + (size_t)ab * p.x_bs;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-
-    for (int kb = grp; kb < nkb; kb += 2) {
-      const int s = kb % TC_STAGES, it = kb / TC_STAGES;
-      const int cc = kb / T, tap = kb - cc * T;
+    int cur_item = -1;
+    bool m_ok = false;
+    int iy0 = 0, ix0 = 0;
+    const float* xb = p.x;
+    auto gather = [&](const TcSeq& sq, float* v) {
+      if (sq.item != cur_item) {  // new work item: decode this thread's output pixel
+        cur_item = sq.item;
+        const int mt = sq.item % m_tiles;
+        const long long mg = (long long)mt * TC_BM2 + row;
+        m_ok = mg < p.M;
+        int ab = 0, aoy = 0, aox = 0;
+        if (m_ok) {
+          ab = (int)(mg / HWo);
+          int rem = (int)(mg - (long long)ab * HWo);
+          aoy = rem / p.Wo;
+          aox = rem - aoy * p.Wo;
+        }
+        iy0 = aoy * p.stride - p.pad; ix0 = aox * p.stride - p.pad;
+        xb = p.x + (size_t)ab * p.x_bs;
+      }
+      const int cc = sq.kb / T, tap = sq.kb - cc * T;
       const int ky = tap / KS, kx = tap - ky * KS;
       const int iy = iy0 + ky * p.dil, ix = ix0 + kx * p.dil;
       const bool ok = m_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
       const int c0 = cc * TC_CK;
       const int nch = min(TC_CK, p.Cin - c0);
       const float* src = xb + (size_t)c0 * HW + (ok ? ((size_t)iy * p.W + ix) : 0);
-      float v[TC_CK];
 #pragma unroll
       for (int j = 0; j < TC_CK; ++j) v[j] = (ok && j < nch) ? __ldg(src + (size_t)j * HW) : 0.f;
-      mbar_wait(empty(s), (uint32_t)((it & 1) ^ 1));
+    };
+
+    float vn[TC_CK];
+    if (seq.valid()) gather(seq, vn);
+    int c = 0;
+    while (seq.valid()) {
+      float v[TC_CK];
+#pragma unroll
+      for (int j = 0; j < TC_CK; ++j) v[j] = vn[j];
+      TcSeq nx = seq;
+      nx.next();
+      if (nx.valid()) gather(nx, vn);  // next block's loads are in flight while this one is converted / stored
+      const int s = c % SA;
+      mbar_wait(a_empty(s), (uint32_t)(((c / SA) & 1) ^ 1));
       tc_fence_after();
+      const uint32_t a_addr = lane_addr + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
       uint32_t hi[TC_CK];
 #pragma unroll
       for (int j = 0; j < TC_CK; ++j) hi[j] = to_tf32(v[j]);
-      const uint32_t a_addr = lane_addr + (uint32_t)(TC_A_COL + s * A_STAGE_COLS);
       tmem_st32(a_addr, hi);
       if (PASSES == 3) {
         uint32_t lo[TC_CK];
@@ -214,86 +267,132 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs p) {
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(a_full(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(s, h));
+      seq = nx;
+      ++c;
     }
-
-    // ======================= epilogue: TMEM -> bias/LeakyReLU/alpha/addend -> NCHW slice =======================
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int ncols = N / 2;  // group 0: columns [0, N/2), group 1: [N/2, N)  (N is a multiple of 16 -> N/2 of 8)
-    const int col_lo = grp * ncols;
-    int bpix_b = 0, bpix = 0;
-    if (m_ok) { bpix_b = ab; bpix = (int)(mg - (long long)ab * HWo); }
-    for (int c = 0; c < ncols; c += 16) {
-      uint32_t r[16];
-      const int col = col_lo + c;
-      tmem_ld16(lane_addr + (uint32_t)(TC_ACC_COL + col), r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m_ok) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c + j >= ncols) break;
-          const int n = nt * N + col + j;
-          if (n < p.Cout) {
-            float val = __uint_as_float(r[j]) + __ldg(p.bias + n);
-            val = leaky(val, p.slope) * p.alpha;
-            if (p.addend) val += __ldg(p.addend + (size_t)bpix_b * p.a_bs + (size_t)n * HWo + bpix);
-            p.y[(size_t)bpix_b * p.y_bs + (size_t)n * HWo + bpix] = val;
-          }
-        }
-      }
-    }
-    tc_fence_before();
   } else if (warp == 8) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
-      // A,B K-major (bits 15,16 = 0), N>>3 in [17,23), M>>4 in [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t d_tmem = tmem_base + TC_ACC_COL;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
-        const int cc = kb / T;
-        const int nch = min(TC_CK, p.Cin - cc * TC_CK);
-        const int nk = (nch + 7) >> 3;
-        mbar_wait(b_full(s), ph);
-        mbar_wait(a_full(s), ph);
+      int c = 0, tcount = 0;
+      if (resident) mbar_wait(b_full(0), 0);
+      while (seq.valid()) {
+        const int buf = NBUF == 2 ? (tcount & 1) : 0;
+        const int use = NBUF == 2 ? (tcount >> 1) : tcount;
+        mbar_wait(acc_empty(buf), (uint32_t)((use & 1) ^ 1));
         tc_fence_after();
-        const uint32_t b_addr = smem_u32(smem_b + (size_t)s * img_bytes);
-        const uint64_t bd_hi = make_b_desc(b_addr);
-        const uint64_t bd_lo = make_b_desc(b_addr + plane_bytes);
-        const uint32_t a_hi = tmem_base + (uint32_t)(TC_A_COL + s * A_STAGE_COLS);
-        for (int j = 0; j < nk; ++j) {
-          const uint64_t koff = (uint64_t)((j * 32) >> 4);  // +32 bytes of K per MMA inside the 128-byte swizzled row
-          if (PASSES == 3) {
-            tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
-            tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
-            tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
+        for (int kb = 0; kb < nkb; ++kb, ++c) {
+          const int s = c % SA;
+          const uint32_t pha = (uint32_t)((c / SA) & 1);
+          const int sb = c % TC_SB;
+          const int cc = kb / T;
+          const int nch = min(TC_CK, p.Cin - cc * TC_CK);
+          const int nk = (nch + 7) >> 3;
+          uint32_t b_addr;
+          if (resident) {
+            b_addr = smem_u32(smem_b + (size_t)kb * img_bytes);
           } else {
-            tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
+            mbar_wait(b_full(sb), (uint32_t)((c / TC_SB) & 1));
+            b_addr = smem_u32(smem_b + (size_t)sb * img_bytes);
           }
+          const uint64_t bd_hi = make_b_desc(b_addr);
+          const uint64_t bd_lo = make_b_desc(b_addr + plane_bytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(a_full(s, h), pha);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + (buf * 2 + h) * acc_stride);
+            const uint32_t a_hi = tmem_base + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
+            for (int j = 0; j < nk; ++j) {
+              const uint64_t koff = (uint64_t)((j * 32) >> 4);  // +32 B of K per MMA inside the 128-byte swizzled row
+              if (PASSES == 3) {
+                tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
+                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
+                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
+              } else {
+                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
+              }
+            }
+          }
+          tc_commit(a_empty(s));
+          if (!resident) tc_commit(b_empty(sb));
         }
-        tc_commit(empty(s));
+        tc_commit(acc_full(buf));
+        ++tcount;
+        seq.item += seq.stride;
       }
-      tc_commit(acc_full);
     }
     __syncwarp();
-  } else {
+  } else if (warp == 9) {
     // ======================= weight loader =======================
     if (lane == 0) {
-      const uint8_t* wsrc = p.wp + (size_t)nt * nkb * img_bytes;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
-        mbar_wait(empty(s), ph ^ 1u);
-        mbar_expect_tx(b_full(s), img_bytes);
-        bulk_g2s(smem_u32(smem_b + (size_t)s * img_bytes), wsrc + (size_t)kb * img_bytes, img_bytes, b_full(s));
+      if (resident) {
+        // n_tiles == 1 in resident mode: one expect_tx for the whole layer, nkb bulk copies
+        mbar_expect_tx(b_full(0), img_bytes * (uint32_t)nkb);
+        for (int kb = 0; kb < nkb; ++kb)
+          bulk_g2s(smem_u32(smem_b + (size_t)kb * img_bytes), p.wp + (size_t)kb * img_bytes, img_bytes, b_full(0));
+      } else {
+        int c = 0;
+        while (seq.valid()) {
+          const int nt = seq.item / m_tiles;
+          const int sb = c % TC_SB;
+          mbar_wait(b_empty(sb), (uint32_t)(((c / TC_SB) & 1) ^ 1));
+          mbar_expect_tx(b_full(sb), img_bytes);
+          bulk_g2s(smem_u32(smem_b + (size_t)sb * img_bytes), p.wp + ((size_t)nt * nkb + seq.kb) * img_bytes, img_bytes,
+                   b_full(sb));
+          seq.next();
+          ++c;
+        }
       }
     }
     __syncwarp();
+  } else if (warp >= 12) {
+    // ======================= epilogue: TMEM -> bias/LeakyReLU/alpha/addend -> NCHW slice =======================
+    const int q = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    int tcount = 0;
+    while (seq.valid()) {
+      const int buf = NBUF == 2 ? (tcount & 1) : 0;
+      const int use = NBUF == 2 ? (tcount >> 1) : tcount;
+      const int mt = seq.item % m_tiles, nt = seq.item / m_tiles;
+      mbar_wait(acc_full(buf), (uint32_t)(use & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const long long mg = (long long)mt * TC_BM2 + h * 128 + q * 32 + lane;
+        const bool m_ok = mg < p.M;
+        int ob = 0, opix = 0;
+        if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
+        const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC_COL + (buf * 2 + h) * acc_stride);
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc_addr + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (m_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = nt * N + c0 + j;
+              if (n < p.Cout) {
+                float val = __uint_as_float(r[j]) + __ldg(p.bias + n);
+                val = leaky(val, p.slope) * p.alpha;
+                if (p.addend) val += __ldg(p.addend + (size_t)ob * p.a_bs + (size_t)n * HWo + opix);
+                p.y[(size_t)ob * p.y_bs + (size_t)n * HWo + opix] = val;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      ++tcount;
+      seq.item += seq.stride;
+    }
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
@@ -331,7 +430,10 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, uint8_t* __restrict_
 bool tc_supported(int Cout, int Cin, int ks, int stride, int dil) {
   (void)stride; (void)dil;
   if (ks != 1 && ks != 3) return false;
-  return Cout >= 16 && Cin >= 16;  // thinner layers are not a real contraction: CUDA-core kernel
+  // Every layer shape of the PWC family maps: Cout is padded to a multiple of 16 (UMMA N), the channel tail of a K
+  // block to a multiple of 8 (UMMA K).  Thin layers (Cout = 1, 2, 3, 9; Cin = 3, 11) waste tensor throughput they do
+  // not need — they are bound by the activation gather, which is identical for any N.
+  return Cout >= 1 && Cin >= 1;
 }
 
 size_t tc_packed_bytes(int Cout, int Cin, int ks, int math) {
@@ -360,8 +462,9 @@ static int launch_tc(const TcArgs& a, size_t smem, cudaStream_t st) {
     }
     attr_smem = smem;
   }
-  dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), a.n_tiles);
-  conv_tc_kernel<KS, PASSES><<<grid, TC_THREADS, smem, st>>>(a);
+  long long items = ((a.M + TC_BM2 - 1) / TC_BM2) * a.n_tiles;
+  int grid = (int)(items < sm_count() ? items : sm_count());  // persistent: one CTA per SM (TMEM: 512 columns each)
+  conv_tc_kernel<KS, PASSES><<<grid, TC_THREADS2, smem, st>>>(a);
   return check_launch("irr_conv2d_fwd");
 }
 
@@ -379,7 +482,10 @@ int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, co
   a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb; a.passes = passes;
   a.M = (long long)B * a.Ho * a.Wo;
   a.slope = slope; a.alpha = alpha;
-  size_t smem = (size_t)TC_STAGES * g.img_bytes + (3 * TC_STAGES + 1) * 8 + 16;
+  size_t total_b = (size_t)g.nkb * g.img_bytes;
+  a.resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX) ? 1 : 0;
+  a.b_smem_bytes = (unsigned)(a.resident ? total_b : (size_t)TC_SB * g.img_bytes);
+  size_t smem = (size_t)a.b_smem_bytes + 24 * 8 + 16;
   if (ks == 1) return passes == 3 ? launch_tc<1, 3>(a, smem, st) : launch_tc<1, 1>(a, smem, st);
   return passes == 3 ? launch_tc<3, 3>(a, smem, st) : launch_tc<3, 1>(a, smem, st);
 }

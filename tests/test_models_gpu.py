@@ -24,8 +24,17 @@ def cat2(rec, key, l, cuda):
     return torch.cat([rec[f"l{l}.{key}_f"], rec[f"l{l}.{key}_b"]], 0).to(cuda).contiguous()
 
 
+@pytest.fixture(scope="module", params=["fp32", "3xtf32"], autouse=True)
+def conv_math(request):
+    """Every model-level test runs twice: CUDA-core fp32 convs and the tcgen05 3xTF32 convs (fp32-grade)."""
+    from irr_b200 import ops, pwc_modules
+    pwc_modules.set_conv_math(ops.MATH_FP32_SIMT if request.param == "fp32" else ops.MATH_TC_3XTF32)
+    yield request.param
+    pwc_modules.set_conv_math(ops.MATH_FP32_SIMT)
+
+
 @pytest.fixture(scope="module", params=[(128, 192), (94, 156)])
-def irr_case(request, cuda):
+def irr_case(request, cuda, conv_math):
     H, W = request.param
     m, p = build("IRR_PWC", cuda)
     i1, i2, gt = O.synthetic_pair(1, H, W, seed=7, max_flow=6.0)
@@ -105,7 +114,8 @@ def test_irr_f6_aliasing_matters(irr_case, cuda):
 def _report(name, got, ref, gt=None):
     d = {k: maxdiff(got[k], ref[k]) for k in ref}
     e = O.epe(got["flow"].cpu(), ref["flow"].cpu()).item()
-    msg = f"[parity] {name}: max-abs {d}  EPE(new,ref)={e:.3e}"
+    from irr_b200 import pwc_modules
+    msg = f"[parity] math={pwc_modules.get_conv_math()} {name}: max-abs {d}  EPE(new,ref)={e:.3e}"
     if gt is not None:
         msg += f"  EPE(new,GT)={O.epe(got['flow'].cpu(), gt).item():.4f} EPE(ref,GT)={O.epe(ref['flow'].cpu(), gt).item():.4f}"
     print(msg)

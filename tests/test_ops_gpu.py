@@ -257,6 +257,10 @@ TC_CASES = [
     (2, 16, 47, 78, 32, 3, 2, 1),      # feature-extractor style stride 2, odd sizes
     (1, 128, 14, 32, 196, 3, 2, 1),    # two N tiles (196 -> 2 x 112)
     (2, 196, 7, 16, 32, 1, 1, 1), (1, 35, 13, 39, 128, 3, 1, 1), (1, 243, 24, 39, 128, 3, 1, 1),
+    # thin layers (N padded to 16 / K tail padded to 8) and >1 work item per CTA (persistent loop, resident weights)
+    (1, 563, 14, 32, 2, 3, 1, 1), (2, 32, 61, 97, 1, 3, 1, 1), (2, 11, 47, 155, 32, 3, 1, 1), (2, 3, 64, 96, 16, 3, 2, 1),
+    (1, 32, 21, 37, 9, 3, 1, 1), (1, 16, 47, 156, 3, 1, 1, 1), (40, 32, 64, 96, 32, 3, 1, 1), (24, 64, 64, 96, 64, 3, 1, 1),
+    (12, 160, 64, 96, 128, 3, 1, 1),
 ]
 
 
@@ -267,7 +271,8 @@ def test_conv2d_tcgen05_vs_torch_cpu(cuda, case, mode):
     B, Cin, H, W, Cout, k, s, d = case
     math = ops.MATH_TC_3XTF32 if mode == "3xtf32" else ops.MATH_TC_TF32
     assert ops.tc_supported(Cout, Cin, k, s, d)
-    x = torch.from_numpy(rs(41, (B, Cin, H, W)))
+    torch.manual_seed(41)
+    x = torch.randn(B, Cin, H, W)
     w = torch.from_numpy(rs(42, (Cout, Cin, k, k))) * float(np.sqrt(2.0 / (Cin * k * k)))
     b = torch.from_numpy(rs(43, (Cout,))) * 0.1
     ref = torch.nn.functional.leaky_relu(
@@ -275,8 +280,11 @@ def test_conv2d_tcgen05_vs_torch_cpu(cuda, case, mode):
     packed = ops.pack_weights(w.to(cuda), math)
     got = ops.conv2d(x.to(cuda), packed, b.to(cuda), Cout, k, s, d, slope=0.1, math=math)
     err = (got.cpu().double() - ref).abs().max().item()
-    print(f"[tc] {case} {mode}: max-abs {err:.3e}")
-    assert err <= (1e-4 if mode == "3xtf32" else 2e-2)
+    refmax = ref.abs().max().item()
+    print(f"[tc] {case} {mode}: max-abs {err:.3e} (|ref|max {refmax:.2f})")
+    # 3xTF32: products are fp32-exact; what remains is the tensor core's fp32 accumulator over K/8 steps.  Gate: 1e-4
+    # abs for O(1) outputs (north_star), scaled with the output magnitude beyond that (N(0,1) inputs reach |y| ~ 6).
+    assert err <= (5e-5 * max(2.0, refmax) if mode == "3xtf32" else 2e-2)
 
 
 def test_conv2d_tcgen05_slices_addend(cuda):
