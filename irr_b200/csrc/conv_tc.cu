@@ -137,6 +137,8 @@ constexpr int TC_THREADS2 = 512;
 constexpr int TC_SB = 4;                   // weight ring depth (streaming mode)
 constexpr size_t TC_RESIDENT_MAX = 168 * 1024;
 
+__device__ float tc_zero_page[32];  // statically zero: source of out-of-image taps
+
 struct TcSeq {  // flat (work item, k block) iterator shared by all roles
   int item, kb, nkb, items, stride;
   __device__ __forceinline__ bool valid() const { return item < items; }
@@ -235,22 +237,20 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       const int iy = iy0 + ky * p.dil, ix = ix0 + kx * p.dil;
       const bool ok = m_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
       const int c0 = cc * TC_CK;
-      const int nch = min(TC_CK, p.Cin - c0);
-      const float* src = xb + (size_t)c0 * HW + (ok ? ((size_t)iy * p.W + ix) : 0);
+      const int nch = p.Cin - c0;
+      // Zero padding without per-element predicates: an out-of-image tap reads a zero page with channel stride 0.
+      const float* src = ok ? xb + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : tc_zero_page;
+      const unsigned cstride = ok ? (unsigned)HW : 0u;
+      if (nch >= TC_CK) {
 #pragma unroll
-      for (int j = 0; j < TC_CK; ++j) v[j] = (ok && j < nch) ? __ldg(src + (size_t)j * HW) : 0.f;
+        for (int j = 0; j < TC_CK; ++j) v[j] = __ldg(src + (size_t)(j * cstride));
+      } else {  // ragged channel tail of the layer: never touch channels beyond the slice
+#pragma unroll
+        for (int j = 0; j < TC_CK; ++j) v[j] = (j < nch) ? __ldg(src + (size_t)(j * cstride)) : 0.f;
+      }
     };
 
-    float vn[TC_CK];
-    if (seq.valid()) gather(seq, vn);
-    int c = 0;
-    while (seq.valid()) {
-      float v[TC_CK];
-#pragma unroll
-      for (int j = 0; j < TC_CK; ++j) v[j] = vn[j];
-      TcSeq nx = seq;
-      nx.next();
-      if (nx.valid()) gather(nx, vn);  // next block's loads are in flight while this one is converted / stored
+    auto convert_store = [&](const float* v, int c) {
       const int s = c % SA;
       mbar_wait(a_empty(s), (uint32_t)(((c / SA) & 1) ^ 1));
       tc_fence_after();
@@ -269,8 +269,24 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(s, h));
-      seq = nx;
+    };
+    // two register buffers, loop unrolled by two: block c+1's loads are in flight while block c is split and stored
+    float va[TC_CK], vb[TC_CK];
+    if (seq.valid()) gather(seq, va);
+    int c = 0;
+    while (seq.valid()) {
+      TcSeq nx = seq;
+      nx.next();
+      if (nx.valid()) gather(nx, vb);
+      convert_store(va, c);
       ++c;
+      if (!nx.valid()) break;
+      seq = nx;
+      nx.next();
+      if (nx.valid()) gather(nx, va);
+      convert_store(vb, c);
+      ++c;
+      seq = nx;
     }
   } else if (warp == 8) {
     // ======================= MMA issuer =======================

@@ -135,60 +135,78 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
           if (gy < H && gx < W) { f1g_off[k] = gy * W + gx; f1ok[k] = 1.f; }
         }
       }
-      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
-        const int s = gchunk % CORR_STAGES;
-        const uint32_t ph = (uint32_t)((gchunk / CORR_STAGES) & 1);
+      // ---- software-pipelined staging: a chunk is 4 load groups (3 halo positions x 8 channels x 4 taps, then the
+      // f1 slots); the loads of group i+1 are issued before group i is combined and stored, so every producer
+      // thread keeps 32-64 independent loads in flight across chunk boundaries.
+      float cur[4 * CC], nxt[4 * CC];
+      auto issue = [&](int ci, int k, float* r) {
         const int c0 = ci * CC;
-        mbar_wait(empty(s), ph ^ 1u);
-        float* st = smem + s * STAGE_ELEMS;
-        // f2 halo: 8 channels of each owned position, loads issued back to back
+        if (k < 3) {
+          const bool live = hp[k].soff >= 0 &&
+                            (hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f);
+          const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (hp[k].soff >= 0) {
-            float v[CC];
+          for (int cc = 0; cc < CC; ++cc) {
+            const bool okc = live && (c0 + cc < C);
+            const float* pc = p + (size_t)cc * HW;
+            r[cc] = okc ? __ldg(pc) : 0.f;
             if (FUSED) {
-              const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
-              float t00[CC], t01[CC], t10[CC], t11[CC];
-#pragma unroll
-              for (int cc = 0; cc < CC; ++cc) {
-                const bool okc = (c0 + cc < C) && (hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f);
-                const float* pc = p + (size_t)cc * HW;
-                t00[cc] = okc ? __ldg(pc) : 0.f;
-                t01[cc] = okc ? __ldg(pc + hp[k].dx) : 0.f;
-                t10[cc] = okc ? __ldg(pc + hp[k].dy) : 0.f;
-                t11[cc] = okc ? __ldg(pc + hp[k].dy + hp[k].dx) : 0.f;
-              }
-#pragma unroll
-              for (int cc = 0; cc < CC; ++cc) {
-                float a = __fmul_rn(t00[cc], hp[k].w00);  // tap order of grid_sampler_2d
-                a = fmaf(t01[cc], hp[k].w01, a);
-                a = fmaf(t10[cc], hp[k].w10, a);
-                v[cc] = fmaf(t11[cc], hp[k].w11, a);
-              }
-            } else {
-              const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
-#pragma unroll
-              for (int cc = 0; cc < CC; ++cc)
-                v[cc] = (hp[k].w00 != 0.f && c0 + cc < C) ? __ldg(p + (size_t)cc * HW) : 0.f;
+              r[CC + cc] = okc ? __ldg(pc + hp[k].dx) : 0.f;
+              r[2 * CC + cc] = okc ? __ldg(pc + hp[k].dy) : 0.f;
+              r[3 * CC + cc] = okc ? __ldg(pc + hp[k].dy + hp[k].dx) : 0.f;
             }
+          }
+        } else {
 #pragma unroll
-            for (int cc = 0; cc < CC; ++cc) st[hp[k].soff + cc * (F2_H * F2_P)] = v[cc];
+          for (int q = 0; q < 2; ++q) {
+            const float* p = f1b + (size_t)c0 * HW + f1g_off[q];
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc)
+              r[q * CC + cc] = (f1s_off[q] >= 0 && f1ok[q] != 0.f && c0 + cc < C) ? __ldg(p + (size_t)cc * HW) : 0.f;
           }
         }
+      };
+      issue(0, 0, nxt);
+      for (int ci = 0; ci < nchunks; ++ci) {
+        const int gc = gchunk + ci;
+        const int s = gc % CORR_STAGES;
+        float* st = smem + s * STAGE_ELEMS;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (f1s_off[k] >= 0) {
-            const float* p = f1b + (size_t)c0 * HW + f1g_off[k];
-            float v[CC];
+        for (int k = 0; k < 4; ++k) {  // fully unrolled: hp[k] stays in registers
 #pragma unroll
-            for (int cc = 0; cc < CC; ++cc) v[cc] = (f1ok[k] != 0.f && c0 + cc < C) ? __ldg(p + (size_t)cc * HW) : 0.f;
+          for (int j = 0; j < 4 * CC; ++j) cur[j] = nxt[j];
+          if (k < 3) issue(ci, k + 1, nxt);
+          else if (ci + 1 < nchunks) issue(ci + 1, 0, nxt);
+          if (k == 0) mbar_wait(empty(s), (uint32_t)(((gc / CORR_STAGES) & 1) ^ 1));
+          if (k < 3) {
+            if (hp[k].soff >= 0) {
 #pragma unroll
-            for (int cc = 0; cc < CC; ++cc) st[f1s_off[k] + cc * (TH * F1_P)] = v[cc];
+              for (int cc = 0; cc < CC; ++cc) {
+                float v;
+                if (FUSED) {
+                  float a = __fmul_rn(cur[cc], hp[k].w00);  // tap order of grid_sampler_2d
+                  a = fmaf(cur[CC + cc], hp[k].w01, a);
+                  a = fmaf(cur[2 * CC + cc], hp[k].w10, a);
+                  v = fmaf(cur[3 * CC + cc], hp[k].w11, a);
+                } else {
+                  v = cur[cc];
+                }
+                st[hp[k].soff + cc * (F2_H * F2_P)] = v;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              if (f1s_off[q] >= 0) {
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) st[f1s_off[q] + cc * (TH * F1_P)] = cur[q * CC + cc];
+              }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full(s));
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full(s));
       }
+      gchunk += nchunks;
     }
   } else {
     // ============================== COMPUTE ==============================
