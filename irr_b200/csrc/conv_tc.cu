@@ -68,6 +68,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One lane of a converged warp (elect.sync): the tcgen05 issue path stays warp-uniform, so its operands live in
+// uniform registers and ptxas does not wrap every UTCHMMA in a per-lane uniformisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -289,8 +301,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       seq = nx;
     }
   } else if (warp == 8) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (whole warp converged; one elected lane issues) =======================
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int c = 0, tcount = 0;
       if (resident) mbar_wait(b_full(0), 0);
@@ -321,26 +333,33 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + (buf * 2 + h) * acc_stride);
             const uint32_t a_hi = tmem_base + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
-            for (int j = 0; j < nk; ++j) {
-              const uint64_t koff = (uint64_t)((j * 32) >> 4);  // +32 B of K per MMA inside the 128-byte swizzled row
-              if (PASSES == 3) {
-                tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
-                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
-                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
-              } else {
-                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
+            if (elect_one()) {
+#pragma unroll 4
+              for (int j = 0; j < nk; ++j) {
+                const uint64_t koff = (uint64_t)(2 * j);  // +32 B of K per MMA inside the 128-byte swizzled row (>>4)
+                if (PASSES == 3) {
+                  tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
+                  tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
+                  tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
+                } else {
+                  tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
+                }
               }
             }
+            __syncwarp();
           }
-          tc_commit(a_empty(s));
-          if (!resident) tc_commit(b_empty(sb));
+          if (elect_one()) {
+            tc_commit(a_empty(s));
+            if (!resident) tc_commit(b_empty(sb));
+          }
+          __syncwarp();
         }
-        tc_commit(acc_full(buf));
+        if (elect_one()) tc_commit(acc_full(buf));
+        __syncwarp();
         ++tcount;
         seq.item += seq.stride;
       }
     }
-    __syncwarp();
   } else if (warp == 9) {
     // ======================= weight loader =======================
     if (lane == 0) {

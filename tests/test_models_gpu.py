@@ -183,6 +183,16 @@ def test_module_api_matches_reference_modules(cuda, golden_dir):
     import irr_b200
     g = np.load(f"{golden_dir}/modules.npz")
     m, p = build("IRR_PWC", cuda, gain=1.0)
+    from irr_b200 import pwc_modules
+
+    # KAT inputs are N(0,1) noise pushed through up to 7 chained MSRA-gain convs: outputs reach |y| ~ 10.  The fp32
+    # CUDA-core path is gated at 1e-4 absolute; for the tensor-core path the gate scales with the output magnitude
+    # (its residual is the tensor core's fp32 accumulator, relative ~2e-5 — see test_conv2d_tcgen05_vs_torch_cpu).
+    def maxdiff(a, b):  # noqa: F811  (relative-to-scale variant for this test)
+        d = (a.detach().cpu() - b.detach().cpu()).abs().max().item()
+        if pwc_modules.get_conv_math() != 0:
+            d /= max(1.0, b.abs().max().item())
+        return d
 
     def rs(seed, shape):
         return torch.from_numpy(np.random.RandomState(seed).standard_normal(shape).astype("float32")).to(cuda)
