@@ -96,11 +96,9 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
+// fp32 -> tf32, round-to-nearest (ties away): add half an ulp of the 10-bit mantissa to the magnitude, drop 13 bits.
+// Two integer ops; ptxas expands cvt.rna.tf32.f32 into ~4 (it also handles Inf/NaN, which activations never are).
+__device__ __forceinline__ uint32_t to_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -186,9 +184,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
   auto acc_full = [&](int b) { return bar0 + 8u * (20 + b); };                    // [20, 22)
   auto acc_empty = [&](int b) { return bar0 + 8u * (22 + b); };                   // [22, 24)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
+  float* bias_all = reinterpret_cast<float*>(bars + 26);  // n_tiles * N floats (<= 256)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  for (int i = tid; i < p.n_tiles * N; i += TC_THREADS2) bias_all[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(a_full(s, 0), 4);
@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       if (PASSES == 3) {
         uint32_t lo[TC_CK];
 #pragma unroll
-        for (int j = 0; j < TC_CK; ++j) lo[j] = to_tf32(v[j] - __uint_as_float(hi[j]));
+        for (int j = 0; j < TC_CK; ++j) lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));  // exact; the tensor
+        // core reads the top 19 bits of it (truncation of an already 2^-12-relative residual: 2^-23 of v, sign-random)
         tmem_st32(a_addr + 32, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       const int buf = NBUF == 2 ? (tcount & 1) : 0;
       const int use = NBUF == 2 ? (tcount >> 1) : tcount;
       const int mt = seq.item % m_tiles, nt = seq.item / m_tiles;
+      const float* bias_s = bias_all + nt * N;
       mbar_wait(acc_full(buf), (uint32_t)(use & 1));
       tc_fence_after();
 #pragma unroll 1
@@ -401,19 +403,25 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
         int ob = 0, opix = 0;
         if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
         const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC_COL + (buf * 2 + h) * acc_stride);
+        const float* ap = p.addend ? p.addend + (size_t)ob * p.a_bs + opix : nullptr;
+        float* yp = p.y + (size_t)ob * p.y_bs + opix;
         for (int c0 = 0; c0 < N; c0 += 16) {
+          const int nb = nt * N + c0;
+          // residual / skip-connection operand: 16 independent loads in flight before the accumulator is touched
+          float add[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            add[j] = (ap != nullptr && m_ok && nb + j < p.Cout) ? __ldg(ap + (size_t)(nb + j) * HWo) : 0.f;
           uint32_t r[16];
           tmem_ld16(acc_addr + (uint32_t)c0, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (m_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int n = nt * N + c0 + j;
-              if (n < p.Cout) {
-                float val = __uint_as_float(r[j]) + __ldg(p.bias + n);
-                val = leaky(val, p.slope) * p.alpha;
-                if (p.addend) val += __ldg(p.addend + (size_t)ob * p.a_bs + (size_t)n * HWo + opix);
-                p.y[(size_t)ob * p.y_bs + (size_t)n * HWo + opix] = val;
+              if (nb + j < p.Cout) {
+                float val = __uint_as_float(r[j]) + bias_s[c0 + j];
+                val = fmaf(leaky(val, p.slope), p.alpha, add[j]);
+                yp[(size_t)(nb + j) * HWo] = val;
               }
             }
           }
@@ -468,7 +476,7 @@ bool tc_supported(int Cout, int Cin, int ks, int stride, int dil) {
   // Every layer shape of the PWC family maps: Cout is padded to a multiple of 16 (UMMA N), the channel tail of a K
   // block to a multiple of 8 (UMMA K).  Thin layers (Cout = 1, 2, 3, 9; Cin = 3, 11) waste tensor throughput they do
   // not need — they are bound by the activation gather, which is identical for any N.
-  return Cout >= 1 && Cin >= 1;
+  return Cout >= 1 && Cout <= 256 && Cin >= 1;
 }
 
 size_t tc_packed_bytes(int Cout, int Cin, int ks, int math) {
@@ -520,7 +528,7 @@ int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, co
   size_t total_b = (size_t)g.nkb * g.img_bytes;
   a.resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX) ? 1 : 0;
   a.b_smem_bytes = (unsigned)(a.resident ? total_b : (size_t)TC_SB * g.img_bytes);
-  size_t smem = (size_t)a.b_smem_bytes + 24 * 8 + 16;
+  size_t smem = (size_t)a.b_smem_bytes + 26 * 8 + 256 * 4 + 64;
   if (ks == 1) return passes == 3 ? launch_tc<1, 3>(a, smem, st) : launch_tc<1, 1>(a, smem, st);
   return passes == 3 ? launch_tc<3, 3>(a, smem, st) : launch_tc<3, 1>(a, smem, st);
 }

@@ -256,13 +256,13 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       const int gy = y0 + r;
       const int gx = x0 + s8 * PX;
       if (gy < H && gx < W) {
-        const float fc = (float)C;
+        const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
         float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
           float v[PX];
 #pragma unroll
-          for (int p = 0; p < PX; ++p) v[p] = leaky(__fdiv_rn(acc[d][p], fc), slope);
+          for (int p = 0; p < PX; ++p) v[p] = leaky(acc[d][p] * inv_c, slope);
           float* q = op + (size_t)d * HW;
           if (vec_ok && gx + PX <= W) {
             reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);

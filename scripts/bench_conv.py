@@ -34,13 +34,14 @@ for i, (B, Cin, H, W, Cout, k, s, d) in enumerate(SHAPES):
             line += f"{m}: n/a  "
             continue
         pk = ops.pack_weights(w, math)
-        y = ops.conv2d(x, pk, b, Cout, k, s, d, math=math)
+        add = torch.randn(B, Cout, Ho, Wo, device=dev) if os.environ.get("IRR_CONV_ADDEND") else None
+        y = ops.conv2d(x, pk, b, Cout, k, s, d, math=math, addend=add, alpha=0.1 if add is not None else 1.0)
         torch.cuda.synchronize()
         n = 3 if only is None else 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            ops.conv2d(x, pk, b, Cout, k, s, d, math=math, out=y)
+            ops.conv2d(x, pk, b, Cout, k, s, d, math=math, out=y, addend=add, alpha=0.1 if add is not None else 1.0)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         err = ""
