@@ -26,6 +26,18 @@ from .pwc_modules import (ContextNetwork, FeatureExtractor, FlowEstimatorDense, 
                           WarpingLayer, conv, flow_scales, initialize_msra)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
 class PWCNet(nn.Module):
     def __init__(self, args=None, div_flow=0.05):
         super().__init__()
@@ -97,18 +109,23 @@ class PWCNet(nn.Module):
         ops.scale_channels(occ_up, out=buf_o[:, 561:562])
         rec("corr", corr); rec("x_1by1", x1by1)
 
-        # flow: dense estimator + residual (:108-111), context + residual (:113-114)
+        # The flow branch (:108-114) and the occlusion branch (:117-123) are independent until the refinement: they run
+        # on two streams (fork/join, also inside a captured CUDA graph) so that at the coarse levels — 7..56 persistent
+        # CTAs per conv — two convs share the 148 SMs instead of running back to back.
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.occ_estimators.forward_into(buf_o, out=buf_o[:, 562:563], addend=buf_o[:, 561:562])
+            occ_cont = self.occ_context_networks(buf_o, addend=buf_o[:, 562:563])
         self.flow_estimators.forward_into(buf_f, out=buf_f[:, 563:565], addend=buf_f[:, 561:563])
         rec("flow_est", buf_f[:, 563:565])
         flow_cont = self.context_networks(buf_f, addend=buf_f[:, 563:565])
         rec("flow_cont", flow_cont)
-        # occlusion (:117-123)
-        self.occ_estimators.forward_into(buf_o, out=buf_o[:, 562:563], addend=buf_o[:, 561:562])
-        occ_cont = self.occ_context_networks(buf_o, addend=buf_o[:, 562:563])
-        rec("occ_cont", occ_cont)
-
         flow = self.refine_flow_stage(flow_cont, x1by1, imgs, height_im, width_im)
         rec("flow", flow)
+        main.wait_stream(side)  # join; occ_cont (allocated on `side`) is only reused by `side` after the next fork
+        rec("occ_cont", occ_cont)
         occ = self.refine_occ_stage(occ_cont, x1by1, flow, height_im, width_im)
         rec("occ", occ)
         return flow, occ

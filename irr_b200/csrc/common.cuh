@@ -46,6 +46,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// Same, for long waits off the critical path (epilogue / loader roles): back off between probes so the spinning warp
+// does not steal issue slots from the producer warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) __nanosleep(128);
+  } while (!done);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Sampling-grid arithmetic of WarpingLayer (models/pwc_modules.py:119-127) + grid_sampler_2d's unnormalise
