@@ -26,7 +26,10 @@ from .pwc_modules import (ContextNetwork, FeatureExtractor, FlowEstimatorDense, 
                           WarpingLayer, conv, flow_scales, initialize_msra)
 
 
+import os
+
 _SIDE_STREAMS = {}
+_USE_SIDE_STREAM = os.environ.get("IRR_NO_SIDE_STREAM", "0") != "1"
 
 
 def _side_stream(device):
@@ -113,7 +116,7 @@ class PWCNet(nn.Module):
         # on two streams (fork/join, also inside a captured CUDA graph) so that at the coarse levels — 7..56 persistent
         # CTAs per conv — two convs share the 148 SMs instead of running back to back.
         main = torch.cuda.current_stream()
-        side = _side_stream(dev)
+        side = _side_stream(dev) if _USE_SIDE_STREAM else main
         side.wait_stream(main)
         with torch.cuda.stream(side):
             self.occ_estimators.forward_into(buf_o, out=buf_o[:, 562:563], addend=buf_o[:, 561:562])

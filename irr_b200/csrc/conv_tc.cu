@@ -250,22 +250,6 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       const bool ok = m_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
       const int c0 = cc * TC_CK;
       const int nch = p.Cin - c0;
-      if (tap == 0 && nch > TC_CK && m_ok) {
-        // First tap of a channel chunk: pull the NEXT chunk's lines (3 rows x <=32 channels around this pixel) into L2
-        // now, so that its first-touch DRAM latency is paid a whole chunk (9 K blocks) before the loads that need it.
-        const int npf = min(TC_CK, nch - TC_CK);
-        const int ixc = ix0 + (KS / 2) * p.dil;
-        if ((unsigned)ixc < (unsigned)p.W) {
-#pragma unroll
-          for (int r = 0; r < KS; ++r) {
-            const int iyr = iy0 + r * p.dil;
-            if ((unsigned)iyr < (unsigned)p.H) {
-              const float* pf = xb + (size_t)(c0 + TC_CK) * HW + ((size_t)iyr * p.W + ixc);
-              for (int j = 0; j < npf; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)j * HW));
-            }
-          }
-        }
-      }
       // Zero padding without per-element predicates: an out-of-image tap reads a zero page with channel stride 0.
       const float* src = ok ? xb + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : tc_zero_page;
       const unsigned cstride = ok ? (unsigned)HW : 0u;
@@ -390,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
         while (seq.valid()) {
           const int nt = seq.item / m_tiles;
           const int sb = c % TC_SB;
-          mbar_wait_backoff(b_empty(sb), (uint32_t)(((c / TC_SB) & 1) ^ 1));
+          mbar_wait(b_empty(sb), (uint32_t)(((c / TC_SB) & 1) ^ 1));
           mbar_expect_tx(b_full(sb), img_bytes);
           bulk_g2s(smem_u32(smem_b + (size_t)sb * img_bytes), p.wp + ((size_t)nt * nkb + seq.kb) * img_bytes, img_bytes,
                    b_full(sb));
@@ -410,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       const int use = NBUF == 2 ? (tcount >> 1) : tcount;
       const int mt = seq.item % m_tiles, nt = seq.item / m_tiles;
       const float* bias_s = bias_all + nt * N;
-      mbar_wait_backoff(acc_full(buf), (uint32_t)(use & 1));
+      mbar_wait(acc_full(buf), (uint32_t)(use & 1));
       tc_fence_after();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
