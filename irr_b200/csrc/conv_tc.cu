@@ -136,8 +136,9 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // Persistent: grid = #SMs; each CTA walks (n tile, 256-pixel M tile) work items.  One work item = two 128-row halves
 // that share every weight stage (halves the weight stream per pixel) and own one TMEM accumulator each.
 //   warps 0-3 : A producers, half 0      warps 4-7 : A producers, half 1
-//   warp 8    : MMA issuer (lane 0)      warp 9    : weight loader (lane 0)
-//   warps 12-15: epilogue (TMEM lane quadrant = warp % 4)
+//   warps 8,9 : MMA issuers, one per half (measured: one issuer spends ~700 clk per K block in mbarrier waits / fences
+//               / elect during which the tensor pipe drains; two issuers on alternate halves keep it fed)
+//   warp 10   : weight loader            warps 12-15: epilogue (TMEM lane quadrant = warp % 4)
 // TMEM columns: [0,256) accumulators (2 halves x N, double-buffered across work items when N <= 64),
 //               [256,512) A ring: stage = 2 halves x (hi 32 | lo 32) columns -> 2 stages (3xTF32) / 4 stages (TF32).
 // Weights: resident in shared memory for the whole kernel when the layer's images fit (K <= ~9 blocks at N=128, every
@@ -193,12 +194,12 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(a_full(s, 0), 4);
       mbar_init(a_full(s, 1), 4);
-      mbar_init(a_empty(s), 1);
+      mbar_init(a_empty(s), 2);  // one tcgen05.commit per MMA issuer (half)
       mbar_init(b_full(s), 1);
-      mbar_init(b_empty(s), 1);
+      mbar_init(b_empty(s), 2);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);
+      mbar_init(acc_full(b), 2);
       mbar_init(acc_empty(b), 4);
     }
     mbar_fence_init();
@@ -301,9 +302,10 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
       ++c;
       seq = nx;
     }
-  } else if (warp == 8) {
-    // ======================= MMA issuer (whole warp converged; one elected lane issues) =======================
+  } else if (warp == 8 || warp == 9) {
+    // ======================= MMA issuers (one per 128-row half; warp converged, one elected lane issues) ==========
     {
+      const int h = warp - 8;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int c = 0, tcount = 0;
       if (resident) mbar_wait(b_full(0), 0);
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
         const int buf = NBUF == 2 ? (tcount & 1) : 0;
         const int use = NBUF == 2 ? (tcount >> 1) : tcount;
         mbar_wait(acc_empty(buf), (uint32_t)((use & 1) ^ 1));
-        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + (buf * 2 + h) * acc_stride);
         for (int kb = 0; kb < nkb; ++kb, ++c) {
           const int s = c % SA;
           const uint32_t pha = (uint32_t)((c / SA) & 1);
@@ -328,40 +330,32 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
           }
           const uint64_t bd_hi = make_b_desc(b_addr);
           const uint64_t bd_lo = make_b_desc(b_addr + plane_bytes);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(a_full(s, h), pha);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + (buf * 2 + h) * acc_stride);
-            const uint32_t a_hi = tmem_base + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
-            if (elect_one()) {
+          const uint32_t a_hi = tmem_base + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
+          mbar_wait(a_full(s, h), pha);
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll 4
-              for (int j = 0; j < nk; ++j) {
-                const uint64_t koff = (uint64_t)(2 * j);  // +32 B of K per MMA inside the 128-byte swizzled row (>>4)
-                if (PASSES == 3) {
-                  tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
-                  tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
-                  tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
-                } else {
-                  tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
-                }
+            for (int j = 0; j < nk; ++j) {
+              const uint64_t koff = (uint64_t)(2 * j);  // +32 B of K per MMA inside the 128-byte swizzled row (>>4)
+              if (PASSES == 3) {
+                tc_mma_ts(d_tmem, a_hi + 32 + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);  // lo * hi
+                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_lo + koff, idesc, 1u);                       // hi * lo
+                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, 1u);                       // hi * hi
+              } else {
+                tc_mma_ts(d_tmem, a_hi + 8 * j, bd_hi + koff, idesc, (kb | j) ? 1u : 0u);
               }
             }
-            __syncwarp();
-          }
-          if (elect_one()) {
             tc_commit(a_empty(s));
             if (!resident) tc_commit(b_empty(sb));
+            if (kb == nkb - 1) tc_commit(acc_full(buf));
           }
           __syncwarp();
         }
-        if (elect_one()) tc_commit(acc_full(buf));
-        __syncwarp();
         ++tcount;
         seq.item += seq.stride;
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 10) {
     // ======================= weight loader =======================
     if (lane == 0) {
       if (resident) {
