@@ -283,12 +283,18 @@ def main():
     ms_e2e = e0.elapsed_time(e1)
 
     # ---- per-kernel timing pass (eager, CUDA events on the launching stream around every launch)
+    # (single stream: with the flow / occlusion branches overlapped on two streams per-launch times are not additive)
+    from irr_b200 import IRR_PWC as _irr_mod
+    import sys as _sys
+    _m = _sys.modules["irr_b200.IRR_PWC"]
+    _m.set_side_stream(False)
     ops.TIMING = []
     nprof = min(args.steps, 3)
     for _ in range(nprof):
         model(inp)
     torch.cuda.synchronize()
     timing, ops.TIMING = ops.TIMING, None
+    _m.set_side_stream(True)
     agg = {}
     for what, meta, s, e in timing:
         agg.setdefault((what, meta), []).append(s.elapsed_time(e))

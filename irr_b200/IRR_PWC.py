@@ -32,6 +32,12 @@ _SIDE_STREAMS = {}
 _USE_SIDE_STREAM = os.environ.get("IRR_NO_SIDE_STREAM", "0") != "1"
 
 
+def set_side_stream(enabled: bool) -> None:
+    """Run the flow and occlusion branches of a level on two streams (default) or serially (per-kernel timing)."""
+    global _USE_SIDE_STREAM
+    _USE_SIDE_STREAM = bool(enabled)
+
+
 def _side_stream(device):
     key = str(device)
     st = _SIDE_STREAMS.get(key)

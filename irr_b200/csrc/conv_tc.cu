@@ -109,6 +109,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
   for (int i = tid; i < p.n_tiles * N; i += TC_THREADS2) bias_all[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(a_full(s, 0), 4);
+      mbar_init(a_full(s, 0), 4);  // 4 producer warps of the group that owns this K block
       mbar_init(a_full(s, 1), 4);
       mbar_init(a_empty(s), 2);  // one tcgen05.commit per MMA issuer (half)
       mbar_init(b_full(s), 1);
@@ -221,86 +229,86 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv_tc_kernel(TcArgs p) {
 
   if (warp < 8) {
     // ======================= A producers =======================
-    const int h = warp >> 2, q = warp & 3;
-    const int row = h * 128 + q * 32 + lane;
+    // Two groups of 4 warps take alternate K blocks (c % 2 == group).  A warp may touch TMEM lanes 32*(warp%4)..+31
+    // only, but in BOTH halves' column ranges — so each thread owns two output pixels (row r of half 0 and row r of
+    // half 1): 64 independent loads in flight per thread, and a full K-block period of slack for the
+    // wait -> split -> tcgen05.st -> wait::st -> arrive chain.
+    const int grp = warp >> 2, q = warp & 3;
     const size_t HW = (size_t)p.H * p.W;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int cur_item = -1;
-    bool m_ok = false;
-    int iy0 = 0, ix0 = 0;
-    const float* xb = p.x;
-    auto gather = [&](const TcSeq& sq, float* v) {
-      if (sq.item != cur_item) {  // new work item: decode this thread's output pixel
-        cur_item = sq.item;
-        const int mt = sq.item % m_tiles;
-        const long long mg = (long long)mt * TC_BM2 + row;
-        m_ok = mg < p.M;
-        int ab = 0, aoy = 0, aox = 0;
-        if (m_ok) {
-          ab = (int)(mg / HWo);
-          int rem = (int)(mg - (long long)ab * HWo);
-          aoy = rem / p.Wo;
-          aox = rem - aoy * p.Wo;
+    bool m_ok[2] = {false, false};
+    int iy0[2] = {0, 0}, ix0[2] = {0, 0};
+    const float* xb[2] = {p.x, p.x};
+    int c = 0;
+    for (; seq.valid(); seq.next(), ++c) {
+      if ((c & 1) != grp) continue;
+      if (seq.item != cur_item) {  // new work item: decode this thread's two output pixels
+        cur_item = seq.item;
+        const int mt = seq.item % m_tiles;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long mg = (long long)mt * TC_BM2 + h * 128 + q * 32 + lane;
+          m_ok[h] = mg < p.M;
+          int ab = 0, aoy = 0, aox = 0;
+          if (m_ok[h]) {
+            ab = (int)(mg / HWo);
+            int rem = (int)(mg - (long long)ab * HWo);
+            aoy = rem / p.Wo;
+            aox = rem - aoy * p.Wo;
+          }
+          iy0[h] = aoy * p.stride - p.pad; ix0[h] = aox * p.stride - p.pad;
+          xb[h] = p.x + (size_t)ab * p.x_bs;
         }
-        iy0 = aoy * p.stride - p.pad; ix0 = aox * p.stride - p.pad;
-        xb = p.x + (size_t)ab * p.x_bs;
       }
-      const int cc = sq.kb / T, tap = sq.kb - cc * T;
+      const int cc = seq.kb / T, tap = seq.kb - cc * T;
       const int ky = tap / KS, kx = tap - ky * KS;
-      const int iy = iy0 + ky * p.dil, ix = ix0 + kx * p.dil;
-      const bool ok = m_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
       const int c0 = cc * TC_CK;
       const int nch = p.Cin - c0;
-      // Zero padding without per-element predicates: an out-of-image tap reads a zero page with channel stride 0.
-      const float* src = ok ? xb + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : tc_zero_page;
-      const unsigned cstride = ok ? (unsigned)HW : 0u;
-      if (nch >= TC_CK) {
+      float v[2][TC_CK];
 #pragma unroll
-        for (int j = 0; j < TC_CK; ++j) v[j] = __ldg(src + (size_t)(j * cstride));
-      } else {  // ragged channel tail of the layer: never touch channels beyond the slice
+      for (int h = 0; h < 2; ++h) {
+        const int iy = iy0[h] + ky * p.dil, ix = ix0[h] + kx * p.dil;
+        const bool ok = m_ok[h] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+        // Zero padding without per-element predicates: an out-of-image tap reads a zero page with channel stride 0.
+        const float* src = ok ? xb[h] + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : tc_zero_page;
+        const unsigned cstride = ok ? (unsigned)HW : 0u;
+        if (nch >= TC_CK) {
 #pragma unroll
-        for (int j = 0; j < TC_CK; ++j) v[j] = (j < nch) ? __ldg(src + (size_t)(j * cstride)) : 0.f;
+          for (int j = 0; j < TC_CK; ++j) v[h][j] = __ldg(src + (size_t)(j * cstride));
+        } else {  // ragged channel tail of the layer: never touch channels beyond the slice
+#pragma unroll
+          for (int j = 0; j < TC_CK; ++j) v[h][j] = (j < nch) ? __ldg(src + (size_t)(j * cstride)) : 0.f;
+        }
       }
-    };
-
-    auto convert_store = [&](const float* v, int c) {
       const int s = c % SA;
       mbar_wait(a_empty(s), (uint32_t)(((c / SA) & 1) ^ 1));
       tc_fence_after();
-      const uint32_t a_addr = lane_addr + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
-      uint32_t hi[TC_CK];
 #pragma unroll
-      for (int j = 0; j < TC_CK; ++j) hi[j] = to_tf32(v[j]);
-      tmem_st32(a_addr, hi);
-      if (PASSES == 3) {
-        uint32_t lo[TC_CK];
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t a_addr = lane_addr + (uint32_t)(TC_A_COL + (s * 2 + h) * A_COLS);
 #pragma unroll
-        for (int j = 0; j < TC_CK; ++j) lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));  // exact; the tensor
-        // core reads the top 19 bits of it (truncation of an already 2^-12-relative residual: 2^-23 of v, sign-random)
-        tmem_st32(a_addr + 32, lo);
+        for (int half = 0; half < 2; ++half) {  // 16 channels at a time bounds the live register set
+          uint32_t hi[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hi[j] = to_tf32(v[h][half * 16 + j]);
+          tmem_st16(a_addr + half * 16, hi);
+          if (PASSES == 3) {
+            uint32_t lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lo[j] = __float_as_uint(v[h][half * 16 + j] - __uint_as_float(hi[j]));  // exact;
+            // the tensor core reads its top 19 bits (truncating an already 2^-12-relative residual: sign-random 2^-23)
+            tmem_st16(a_addr + 32 + half * 16, lo);
+          }
+        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(s, h));
-    };
-    // two register buffers, loop unrolled by two: block c+1's loads are in flight while block c is split and stored
-    float va[TC_CK], vb[TC_CK];
-    if (seq.valid()) gather(seq, va);
-    int c = 0;
-    while (seq.valid()) {
-      TcSeq nx = seq;
-      nx.next();
-      if (nx.valid()) gather(nx, vb);
-      convert_store(va, c);
-      ++c;
-      if (!nx.valid()) break;
-      seq = nx;
-      nx.next();
-      if (nx.valid()) gather(nx, va);
-      convert_store(vb, c);
-      ++c;
-      seq = nx;
+      if (lane == 0) {
+        mbar_arrive(a_full(s, 0));
+        mbar_arrive(a_full(s, 1));
+      }
     }
   } else if (warp == 8 || warp == 9) {
     // ======================= MMA issuers (one per 128-row half; warp converged, one elected lane issues) ==========

@@ -166,45 +166,49 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
           }
         }
       };
-      issue(0, 0, nxt);
+      // two register buffers used alternately (no copy: copying a load destination would wait for the load)
+      auto consume = [&](int k, const float* r, float* st, int s) {
+        if (k < 3) {
+          if (hp[k].soff >= 0) {
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+              float v;
+              if (FUSED) {
+                float a = __fmul_rn(r[cc], hp[k].w00);  // tap order of grid_sampler_2d
+                a = fmaf(r[CC + cc], hp[k].w01, a);
+                a = fmaf(r[2 * CC + cc], hp[k].w10, a);
+                v = fmaf(r[3 * CC + cc], hp[k].w11, a);
+              } else {
+                v = r[cc];
+              }
+              st[hp[k].soff + cc * (F2_H * F2_P)] = v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (f1s_off[q] >= 0) {
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) st[f1s_off[q] + cc * (TH * F1_P)] = r[q * CC + cc];
+            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full(s));
+        }
+      };
+      issue(0, 0, cur);
       for (int ci = 0; ci < nchunks; ++ci) {
         const int gc = gchunk + ci;
         const int s = gc % CORR_STAGES;
         float* st = smem + s * STAGE_ELEMS;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // fully unrolled: hp[k] stays in registers
-#pragma unroll
-          for (int j = 0; j < 4 * CC; ++j) cur[j] = nxt[j];
-          if (k < 3) issue(ci, k + 1, nxt);
-          else if (ci + 1 < nchunks) issue(ci + 1, 0, nxt);
-          if (k == 0) mbar_wait(empty(s), (uint32_t)(((gc / CORR_STAGES) & 1) ^ 1));
-          if (k < 3) {
-            if (hp[k].soff >= 0) {
-#pragma unroll
-              for (int cc = 0; cc < CC; ++cc) {
-                float v;
-                if (FUSED) {
-                  float a = __fmul_rn(cur[cc], hp[k].w00);  // tap order of grid_sampler_2d
-                  a = fmaf(cur[CC + cc], hp[k].w01, a);
-                  a = fmaf(cur[2 * CC + cc], hp[k].w10, a);
-                  v = fmaf(cur[3 * CC + cc], hp[k].w11, a);
-                } else {
-                  v = cur[cc];
-                }
-                st[hp[k].soff + cc * (F2_H * F2_P)] = v;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              if (f1s_off[q] >= 0) {
-#pragma unroll
-                for (int cc = 0; cc < CC; ++cc) st[f1s_off[q] + cc * (TH * F1_P)] = cur[q * CC + cc];
-              }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full(s));
-          }
-        }
+        issue(ci, 1, nxt);
+        mbar_wait(empty(s), (uint32_t)(((gc / CORR_STAGES) & 1) ^ 1));
+        consume(0, cur, st, s);
+        issue(ci, 2, cur);
+        consume(1, nxt, st, s);
+        issue(ci, 3, nxt);
+        consume(2, cur, st, s);
+        if (ci + 1 < nchunks) issue(ci + 1, 0, cur);
+        consume(3, nxt, st, s);
       }
       gchunk += nchunks;
     }
