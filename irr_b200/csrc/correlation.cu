@@ -42,6 +42,8 @@ constexpr int NHALO = F2_H * F2_WV;         // 640
 constexpr int NF1 = TH * TW;                // 256
 constexpr int CORR_SMEM = CORR_STAGES * STAGE_ELEMS * 4 + 2 * CORR_STAGES * 8;
 
+__device__ float corr_zero_page[32];  // statically zero: source of dead halo positions
+
 struct ProdPos {  // one halo (or f1) position owned by a producer thread
   int soff;       // offset inside the stage for channel 0 (floats); < 0 => unused slot
   int goff;       // global offset (y*W + x), clamped; for fused: clamped (y0*W + x0)
@@ -139,30 +141,66 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       // f1 slots); the loads of group i+1 are issued before group i is combined and stored, so every producer
       // thread keeps 32-64 independent loads in flight across chunk boundaries.
       float cur[4 * CC], nxt[4 * CC];
+      // Per-position source pointers with the predicates folded in: a dead position (outside the image, masked out,
+      // or an unused slot) reads a zero page with channel stride 0, so the steady-state loads carry no predicate and
+      // cost IMAD.WIDE + LDG each.
+      const float* hb[3];
+      unsigned hcs[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const bool live = hp[k].soff >= 0 &&
+                          (hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f);
+        hb[k] = live ? f2b + hp[k].goff : corr_zero_page;
+        hcs[k] = live ? (unsigned)HW : 0u;
+        if (!live) { hp[k].dx = 0; hp[k].dy = 0; }
+      }
+      const float* fb[2];
+      unsigned fcs[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const bool live = f1s_off[q] >= 0 && f1ok[q] != 0.f;
+        fb[q] = live ? f1b + f1g_off[q] : corr_zero_page;
+        fcs[q] = live ? (unsigned)HW : 0u;
+      }
       auto issue = [&](int ci, int k, float* r) {
         const int c0 = ci * CC;
+        const bool full_chunk = c0 + CC <= C;
         if (k < 3) {
-          const bool live = hp[k].soff >= 0 &&
-                            (hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f);
-          const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
+          const float* p = hb[k] + (size_t)c0 * hcs[k];
+          const float* p01 = p + hp[k].dx;
+          const float* p10 = p + hp[k].dy;
+          const float* p11 = p10 + hp[k].dx;
+          if (full_chunk) {
 #pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            const bool okc = live && (c0 + cc < C);
-            const float* pc = p + (size_t)cc * HW;
-            r[cc] = okc ? __ldg(pc) : 0.f;
-            if (FUSED) {
-              r[CC + cc] = okc ? __ldg(pc + hp[k].dx) : 0.f;
-              r[2 * CC + cc] = okc ? __ldg(pc + hp[k].dy) : 0.f;
-              r[3 * CC + cc] = okc ? __ldg(pc + hp[k].dy + hp[k].dx) : 0.f;
+            for (int cc = 0; cc < CC; ++cc) {
+              const unsigned o = (unsigned)cc * hcs[k];
+              r[cc] = __ldg(p + o);
+              if (FUSED) {
+                r[CC + cc] = __ldg(p01 + o);
+                r[2 * CC + cc] = __ldg(p10 + o);
+                r[3 * CC + cc] = __ldg(p11 + o);
+              }
+            }
+          } else {  // ragged channel tail
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+              const bool okc = c0 + cc < C;
+              const unsigned o = (unsigned)cc * hcs[k];
+              r[cc] = okc ? __ldg(p + o) : 0.f;
+              if (FUSED) {
+                r[CC + cc] = okc ? __ldg(p01 + o) : 0.f;
+                r[2 * CC + cc] = okc ? __ldg(p10 + o) : 0.f;
+                r[3 * CC + cc] = okc ? __ldg(p11 + o) : 0.f;
+              }
             }
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const float* p = f1b + (size_t)c0 * HW + f1g_off[q];
+            const float* p = fb[q] + (size_t)c0 * fcs[q];
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc)
-              r[q * CC + cc] = (f1s_off[q] >= 0 && f1ok[q] != 0.f && c0 + cc < C) ? __ldg(p + (size_t)cc * HW) : 0.f;
+              r[q * CC + cc] = (full_chunk || c0 + cc < C) ? __ldg(p + (unsigned)cc * fcs[q]) : 0.f;
           }
         }
       };
