@@ -10,12 +10,13 @@
 //     fp32 accumulators per thread, so one channel step is 2 + 4 LDS.128 for 72 FFMA — the register tile that keeps
 //     the FMA pipe, not the LSU, the limiter (the reference kernel does 1 FMA per 2 global loads and re-reads f1 81x).
 //   * warps 9-15 = PRODUCERS: they stage 8-channel chunks of the f1 tile [8][8][36] and the f2 halo tile [8][16][44]
-//     into a 3-stage shared-memory ring (mbarrier full/empty), running ahead of the compute warps — across tile
-//     boundaries too, so the epilogue of tile t overlaps the loads of tile t+1.  Each producer thread owns <= 3 fixed
-//     halo positions: in the fused-warp variant it computes the sample coordinates / bilinear weights / hard mask of
-//     those positions ONCE per tile (bit-exact recipe in common.cuh), keeps them in registers and issues the 4-tap
-//     gathers of all 8 channels of a chunk back to back (32 independent loads in flight per thread).  The warped
-//     tensor never exists in HBM.
+//     into a 3-slot shared-memory ring (mbarrier full/empty) with cp.async (16-byte, zero-fill = the zero padding),
+//     one chunk ahead of the compute warps and across tile boundaries, so the epilogue of tile t overlaps the loads
+//     of tile t+1.  Fused variant: the sample coordinates / bilinear weights / hard mask of each halo position are
+//     computed ONCE per tile (bit-exact recipe in common.cuh) and kept in registers; the tile's source footprint of f2
+//     (24 x 48 texels per channel, placed from the min/max of the sample coordinates) is copied asynchronously into a
+//     second ring and the four taps are read from shared memory; a tile whose flow is too divergent for the window
+//     gathers from global memory instead.  The warped tensor never exists in HBM.
 //   * row pitches 36 / 44 words (== 4, 12 mod 32) make every quarter-warp LDS.128 (8 rows, same strip) conflict-free.
 //   * global reads are coalesced along W; f2's 2.5x halo re-read is served by the 126 MB L2 (the largest level-4 map
 //     of cfg 3 is 28.6 MB), so DRAM traffic stays at the algorithmic B*H*W*(8C+324) bytes.
@@ -40,7 +41,17 @@ constexpr int F2_ELEMS = CC * F2_H * F2_P;  // 5632
 constexpr int STAGE_ELEMS = F1_ELEMS + F2_ELEMS;
 constexpr int NHALO = F2_H * F2_WV;         // 640
 constexpr int NF1 = TH * TW;                // 256
-constexpr int CORR_SMEM = CORR_STAGES * STAGE_ELEMS * 4 + 2 * CORR_STAGES * 8;
+constexpr int FP_H = 24, FP_W = 48;            // fused variant: source footprint window per channel (texels)
+constexpr int FP_ELEMS = CC * FP_H * FP_W;     // 9216 floats per ring slot
+constexpr int CORR_SMEM_PLAIN = CORR_STAGES * STAGE_ELEMS * 4 + 64;
+constexpr int CORR_SMEM_FUSED = CORR_SMEM_PLAIN + CORR_STAGES * FP_ELEMS * 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
 
 __device__ float corr_zero_page[32];  // statically zero: source of dead halo positions
 
@@ -55,7 +66,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(CORR_THREADS, 1)
     corr_kernel(const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                 const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
-                GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
+                GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int vec_in, int tiles_x, int tiles_y,
                 int ntiles) {
   extern __shared__ __align__(16) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CORR_STAGES * STAGE_ELEMS);
@@ -77,9 +88,19 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
 
   if (tid >= NCOMP) {
     // ============================== PRODUCERS ==============================
+    // Staging is asynchronous: every plain copy is a cp.async (16 B when rows are 16-byte aligned, else 4 B) with
+    // zero-fill for the out-of-image part, issued two chunks ahead, so no producer thread ever waits on a global load.
+    //   * f1 tile and, without a warp, the f2 halo tile land directly in their slot of the ring;
+    //   * with the warp fused in, the tile's SOURCE FOOTPRINT of f2 (the halo box displaced by the flow, 24 x 48 texels
+    //     per channel, positioned per tile from the min/max of the sample coordinates) is copied into a second ring and
+    //     the four bilinear taps are read from shared memory (LDS latency instead of a DRAM round trip per tap group);
+    //     tiles whose flow field is too divergent for the footprint fall back to gathering from global memory.
     const int pt = tid - NCOMP;
     const int lane = tid & 31;
+    float* fpr = smem + CORR_STAGES * STAGE_ELEMS + 16;           // footprint ring (FUSED only), after the barriers
+    int* red = reinterpret_cast<int*>(smem + CORR_STAGES * STAGE_ELEMS + 12);  // 4 ints: ymin, ymax, xmin, xmax
     int gchunk = 0;
+    auto prod_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"); };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
@@ -89,164 +110,182 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       if (b2 >= B) b2 -= B;
       const float* f1b = f1 + (size_t)b * f1_bs;
       const float* f2b = f2 + (size_t)b2 * f2_bs;
-      // ---- positions owned by this thread: up to 3 f2 halo slots + up to 2 f1 slots (balanced: 3+1 or 2+2)
+
+      // ---- per-tile: sample taps of the (<= 3) halo positions this thread owns
       ProdPos hp[3];
+      int ya_[3], xa_[3];
+      int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int h = pt + k * NPROD;
         ProdPos q;
         q.soff = -1; q.goff = 0; q.dx = 0; q.dy = 0; q.w00 = q.w01 = q.w10 = q.w11 = 0.f;
+        ya_[k] = 0; xa_[k] = 0;
         if (h < NHALO) {
           const int hr = h / F2_WV, hx = h - hr * F2_WV;
           const int gy = y0 - MD + hr, gx = x0 - MD + hx;
           q.soff = F1_ELEMS + hr * F2_P + hx;
-          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            if (FUSED) {
-              const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * W + gx;
-              float ix, iy;
-              sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
-              Taps tp = make_taps(ix, iy, W, H);
-              if (tp.mask != 0.f) {
-                const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
-                const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
-                q.goff = ya * W + xa;
-                q.dx = (xb != xa) ? 1 : 0;
-                q.dy = (yb != ya) ? W : 0;
-                // a clamped (out-of-range) tap has zero weight (make_taps), so aliasing it onto its in-range
-                // neighbour's address is harmless: the four reads are always in bounds.
-                q.w00 = tp.w00; q.w01 = tp.w01; q.w10 = tp.w10; q.w11 = tp.w11;
-              }
-            } else {
-              q.goff = gy * W + gx;
-              q.w00 = 1.f;
+          if (FUSED && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * W + gx;
+            float ix, iy;
+            sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
+            Taps tp = make_taps(ix, iy, W, H);
+            if (tp.mask != 0.f) {
+              const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
+              const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
+              ya_[k] = ya; xa_[k] = xa;
+              q.goff = ya * W + xa;
+              q.dx = (xb != xa) ? 1 : 0;
+              q.dy = (yb != ya) ? 1 : 0;  // in rows; scaled by the row pitch of whichever source is sampled
+              // a clamped (out-of-range) tap has zero weight (make_taps), so aliasing it onto its in-range neighbour's
+              // address is harmless: the four reads are always in bounds.
+              q.w00 = tp.w00; q.w01 = tp.w01; q.w10 = tp.w10; q.w11 = tp.w11;
+              lo_y = min(lo_y, ya); hi_y = max(hi_y, yb); lo_x = min(lo_x, xa); hi_x = max(hi_x, xb);
             }
           }
         }
         hp[k] = q;
       }
-      int f1s_off[2], f1g_off[2];
-      float f1ok[2];
+      // ---- FUSED: does the tile's sample footprint fit the shared-memory window?
+      bool foot = false;
+      int oy = 0, ox = 0;
+      if (FUSED) {
+        if (pt == 0) { red[0] = 1 << 30; red[1] = -1; red[2] = 1 << 30; red[3] = -1; }
+        prod_sync();
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        int q = (k == 0) ? pt : (pt >= 192 ? NPROD + (pt - 192) : -1);
-        f1s_off[k] = -1; f1g_off[k] = 0; f1ok[k] = 0.f;
-        if (q >= 0 && q < NF1) {
-          const int rr = q >> 5, xx = q & 31;
-          const int gy = y0 + rr, gx = x0 + xx;
-          f1s_off[k] = rr * F1_P + xx;
-          if (gy < H && gx < W) { f1g_off[k] = gy * W + gx; f1ok[k] = 1.f; }
+        for (int o = 16; o > 0; o >>= 1) {
+          lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+          lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
         }
+        if (lane == 0) { atomicMin(&red[0], lo_y); atomicMax(&red[1], hi_y); atomicMin(&red[2], lo_x); atomicMax(&red[3], hi_x); }
+        prod_sync();
+        const int ymin = red[0], ymax = red[1], xmin = red[2], xmax = red[3];
+        const bool any_live = ymax >= ymin;
+        oy = any_live ? ymin : 0; ox = any_live ? (xmin & ~3) : 0;
+        foot = vec_in && (!any_live || ((ymax - oy) < FP_H && (xmax - ox) < FP_W));
+        prod_sync();  // red[] is re-initialised by the next tile
       }
-      // ---- software-pipelined staging: a chunk is 4 load groups (3 halo positions x 8 channels x 4 taps, then the
-      // f1 slots); the loads of group i+1 are issued before group i is combined and stored, so every producer
-      // thread keeps 32-64 independent loads in flight across chunk boundaries.
-      float cur[4 * CC], nxt[4 * CC];
-      // Per-position source pointers with the predicates folded in: a dead position (outside the image, masked out,
-      // or an unused slot) reads a zero page with channel stride 0, so the steady-state loads carry no predicate and
-      // cost IMAD.WIDE + LDG each.
-      const float* hb[3];
-      unsigned hcs[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const bool live = hp[k].soff >= 0 &&
-                          (hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f);
-        hb[k] = live ? f2b + hp[k].goff : corr_zero_page;
-        hcs[k] = live ? (unsigned)HW : 0u;
-        if (!live) { hp[k].dx = 0; hp[k].dy = 0; }
-      }
-      const float* fb[2];
-      unsigned fcs[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const bool live = f1s_off[q] >= 0 && f1ok[q] != 0.f;
-        fb[q] = live ? f1b + f1g_off[q] : corr_zero_page;
-        fcs[q] = live ? (unsigned)HW : 0u;
-      }
-      auto issue = [&](int ci, int k, float* r) {
+
+      // ---- copy issue for one chunk (ring slot s), cooperative over the 224 producer threads
+      auto issue_copies = [&](int ci, int s) {
         const int c0 = ci * CC;
-        const bool full_chunk = c0 + CC <= C;
-        if (k < 3) {
-          const float* p = hb[k] + (size_t)c0 * hcs[k];
-          const float* p01 = p + hp[k].dx;
-          const float* p10 = p + hp[k].dy;
-          const float* p11 = p10 + hp[k].dx;
-          if (full_chunk) {
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc) {
-              const unsigned o = (unsigned)cc * hcs[k];
-              r[cc] = __ldg(p + o);
-              if (FUSED) {
-                r[CC + cc] = __ldg(p01 + o);
-                r[2 * CC + cc] = __ldg(p10 + o);
-                r[3 * CC + cc] = __ldg(p11 + o);
-              }
+        float* st = smem + s * STAGE_ELEMS;
+        if (vec_in) {
+          for (int j = pt; j < CC * TH * (TW / 4); j += NPROD) {  // f1: 8 ch x 8 rows x 8 float4
+            const int xq = j & 7, rr = (j >> 3) & 7, cc = j >> 6;
+            const int gy = y0 + rr, gx = x0 + xq * 4, c = c0 + cc;
+            const bool ok = c < C && gy < H && gx < W;
+            cp_async16(smem_u32(st + (cc * TH + rr) * F1_P + xq * 4), ok ? f1b + (size_t)c * HW + (size_t)gy * W + gx : f1b, ok);
+          }
+          if (!FUSED) {
+            for (int j = pt; j < CC * F2_H * (F2_WV / 4); j += NPROD) {  // f2 halo: 8 ch x 16 rows x 10 float4
+              const int cc = j / (F2_H * 10), r2 = j - cc * (F2_H * 10);
+              const int hr = r2 / 10, xq = r2 - hr * 10;
+              const int gy = y0 - MD + hr, gx = x0 - MD + xq * 4, c = c0 + cc;
+              const bool ok = c < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+              cp_async16(smem_u32(st + F1_ELEMS + (cc * F2_H + hr) * F2_P + xq * 4), ok ? f2b + (size_t)c * HW + (size_t)gy * W + gx : f2b, ok);
             }
-          } else {  // ragged channel tail
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc) {
-              const bool okc = c0 + cc < C;
-              const unsigned o = (unsigned)cc * hcs[k];
-              r[cc] = okc ? __ldg(p + o) : 0.f;
-              if (FUSED) {
-                r[CC + cc] = okc ? __ldg(p01 + o) : 0.f;
-                r[2 * CC + cc] = okc ? __ldg(p10 + o) : 0.f;
-                r[3 * CC + cc] = okc ? __ldg(p11 + o) : 0.f;
-              }
+          } else if (foot) {
+            float* fp = fpr + s * FP_ELEMS;
+            for (int j = pt; j < CC * FP_H * (FP_W / 4); j += NPROD) {  // footprint: 8 ch x 24 rows x 12 float4
+              const int cc = j / (FP_H * (FP_W / 4)), r2 = j - cc * (FP_H * (FP_W / 4));
+              const int fr = r2 / (FP_W / 4), xq = r2 - fr * (FP_W / 4);
+              const int gy = oy + fr, gx = ox + xq * 4, c = c0 + cc;
+              const bool ok = c < C && gy < H && gx < W;  // oy, ox >= 0
+              cp_async16(smem_u32(fp + (cc * FP_H + fr) * FP_W + xq * 4), ok ? f2b + (size_t)c * HW + (size_t)gy * W + gx : f2b, ok);
             }
           }
         } else {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float* p = fb[q] + (size_t)c0 * fcs[q];
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc)
-              r[q * CC + cc] = (full_chunk || c0 + cc < C) ? __ldg(p + (unsigned)cc * fcs[q]) : 0.f;
+          for (int j = pt; j < CC * TH * TW; j += NPROD) {
+            const int xx = j & 31, rr = (j >> 5) & 7, cc = j >> 8;
+            const int gy = y0 + rr, gx = x0 + xx, c = c0 + cc;
+            const bool ok = c < C && gy < H && gx < W;
+            cp_async4(smem_u32(st + (cc * TH + rr) * F1_P + xx), ok ? f1b + (size_t)c * HW + (size_t)gy * W + gx : f1b, ok);
           }
-        }
-      };
-      // two register buffers used alternately (no copy: copying a load destination would wait for the load)
-      auto consume = [&](int k, const float* r, float* st, int s) {
-        if (k < 3) {
-          if (hp[k].soff >= 0) {
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc) {
-              float v;
-              if (FUSED) {
-                float a = __fmul_rn(r[cc], hp[k].w00);  // tap order of grid_sampler_2d
-                a = fmaf(r[CC + cc], hp[k].w01, a);
-                a = fmaf(r[2 * CC + cc], hp[k].w10, a);
-                v = fmaf(r[3 * CC + cc], hp[k].w11, a);
-              } else {
-                v = r[cc];
-              }
-              st[hp[k].soff + cc * (F2_H * F2_P)] = v;
+          if (!FUSED) {
+            for (int j = pt; j < CC * NHALO; j += NPROD) {
+              const int cc = j / NHALO, h2 = j - cc * NHALO;
+              const int hr = h2 / F2_WV, hx = h2 - hr * F2_WV;
+              const int gy = y0 - MD + hr, gx = x0 - MD + hx, c = c0 + cc;
+              const bool ok = c < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+              cp_async4(smem_u32(st + F1_ELEMS + (cc * F2_H + hr) * F2_P + hx), ok ? f2b + (size_t)c * HW + (size_t)gy * W + gx : f2b, ok);
             }
           }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-            if (f1s_off[q] >= 0) {
-#pragma unroll
-              for (int cc = 0; cc < CC; ++cc) st[f1s_off[q] + cc * (TH * F1_P)] = r[q * CC + cc];
-            }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full(s));
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      issue(0, 0, cur);
+
+      // ---- pipeline: copies for chunk ci+1 are in flight while chunk ci is finished (sampled) and published
+      {
+        const int s0 = gchunk % CORR_STAGES;
+        mbar_wait(empty(s0), (uint32_t)(((gchunk / CORR_STAGES) & 1) ^ 1));
+        issue_copies(0, s0);
+      }
       for (int ci = 0; ci < nchunks; ++ci) {
         const int gc = gchunk + ci;
         const int s = gc % CORR_STAGES;
         float* st = smem + s * STAGE_ELEMS;
-        issue(ci, 1, nxt);
-        mbar_wait(empty(s), (uint32_t)(((gc / CORR_STAGES) & 1) ^ 1));
-        consume(0, cur, st, s);
-        issue(ci, 2, cur);
-        consume(1, nxt, st, s);
-        issue(ci, 3, nxt);
-        consume(2, cur, st, s);
-        if (ci + 1 < nchunks) issue(ci + 1, 0, cur);
-        consume(3, nxt, st, s);
+        if (ci + 1 < nchunks) {
+          const int s1 = (gc + 1) % CORR_STAGES;
+          mbar_wait(empty(s1), (uint32_t)((((gc + 1) / CORR_STAGES) & 1) ^ 1));
+          issue_copies(ci + 1, s1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        if (FUSED) {
+          const int c0 = ci * CC;
+          if (foot) {
+            prod_sync();  // every producer's share of the footprint has landed
+            const float* fp = fpr + s * FP_ELEMS;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (hp[k].soff >= 0) {
+                const bool live = hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f;
+                // dead positions (outside the image / masked out) sample nothing: keep the address inside the window
+                const float* p = fp + (live ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : 0);
+                const int dx = live ? hp[k].dx : 0, dy = live ? hp[k].dy * FP_W : 0;
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) {
+                  const float* pc = p + cc * (FP_H * FP_W);
+                  float a = __fmul_rn(pc[0], hp[k].w00);  // tap order of grid_sampler_2d
+                  a = fmaf(pc[dx], hp[k].w01, a);
+                  a = fmaf(pc[dy], hp[k].w10, a);
+                  a = fmaf(pc[dy + dx], hp[k].w11, a);
+                  st[hp[k].soff + cc * (F2_H * F2_P)] = live ? a : 0.f;
+                }
+              }
+            }
+          } else {  // divergent flow (or unaligned rows): gather the taps from global memory
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (hp[k].soff >= 0) {
+                const bool live = hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f;
+                const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
+                const int dx = hp[k].dx, dy = hp[k].dy * W;
+                float t[4][CC];
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) {
+                  const bool okc = live && (c0 + cc < C);
+                  const float* pc = p + (size_t)cc * HW;
+                  t[0][cc] = okc ? __ldg(pc) : 0.f;
+                  t[1][cc] = okc ? __ldg(pc + dx) : 0.f;
+                  t[2][cc] = okc ? __ldg(pc + dy) : 0.f;
+                  t[3][cc] = okc ? __ldg(pc + dy + dx) : 0.f;
+                }
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) {
+                  float a = __fmul_rn(t[0][cc], hp[k].w00);
+                  a = fmaf(t[1][cc], hp[k].w01, a);
+                  a = fmaf(t[2][cc], hp[k].w10, a);
+                  st[hp[k].soff + cc * (F2_H * F2_P)] = fmaf(t[3][cc], hp[k].w11, a);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full(s));
       }
       gchunk += nchunks;
     }
@@ -266,6 +305,33 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       for (int d = 0; d < ND; ++d)
 #pragma unroll
         for (int p = 0; p < PX; ++p) acc[d][p] = 0.f;
+
+      {  // The compute warps spend most of a tile waiting on the producers: use them to pull the NEXT tile's f1 rows and
+         // (un-warped) f2 neighbourhood into L2, so the producers' gathers find their lines there instead of in DRAM.
+        const int ntile = tile + (int)gridDim.x;
+        if (ntile < ntiles) {
+          const int ntx = ntile % tiles_x, nty = (ntile / tiles_x) % tiles_y, nb = ntile / (tiles_x * tiles_y);
+          int nb2 = nb + shift;
+          if (nb2 >= B) nb2 -= B;
+          const float* pf1 = f1 + (size_t)nb * f1_bs;
+          const float* pf2 = f2 + (size_t)nb2 * f2_bs;
+          const int ny0 = nty * TH, nx0 = ntx * TW;
+          for (int i = tid; i < C * 40; i += NCOMP) {
+            const int c = i / 40, rr = i - c * 40;
+            const float* a;
+            if (rr < 8) {
+              const int y = min(ny0 + rr, H - 1);
+              a = pf1 + (size_t)c * HW + (size_t)y * W + min(nx0, W - 1);
+            } else {
+              const int k = rr - 8;
+              const int y = min(max(ny0 - MD + (k >> 1), 0), H - 1);
+              const int x = min(max(nx0 - MD + (k & 1) * 32, 0), W - 1);
+              a = pf2 + (size_t)c * HW + (size_t)y * W + x;
+            }
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
+      }
 
       for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
         const int s = gchunk % CORR_STAGES;
@@ -355,6 +421,7 @@ template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
                        int C, int H, int W, int shift, float slope, cudaStream_t st) {
+  constexpr int CORR_SMEM = FUSED ? CORR_SMEM_FUSED : CORR_SMEM_PLAIN;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(corr_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
@@ -365,13 +432,16 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
     attr_done = true;
   }
   int vec_ok = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  // 16-byte cp.async staging needs 16-byte aligned rows in both operands
+  int vec_in = (W % 4 == 0) && (f1_bs % 4 == 0) && (f2_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(f2) & 15) == 0);
   int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   long long nt = (long long)tiles_x * tiles_y * B;
   if (nt > 0x7fffffffLL) return fail_arg(fn, "too many tiles");
   int ntiles = (int)nt;
   int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
   corr_kernel<FUSED><<<grid, CORR_THREADS, CORR_SMEM, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H,
-                                                            W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles);
+                                                            W, shift, slope, vec_ok, vec_in, tiles_x, tiles_y, ntiles);
   return check_launch(fn);
 }
 
