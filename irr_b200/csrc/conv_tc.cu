@@ -16,11 +16,10 @@
 //     per K block completing on an mbarrier — no tensor map, no per-element work.
 //   * K order is (channel chunk outer, tap inner): the nine taps of a chunk re-read the same activation lines, which
 //     stay in L1; L2 sees each activation ~once and the weight stream once per CTA.
-//   * warp roles: warps 0-7 = A producers (two groups alternating K blocks; a warp may only touch TMEM lanes
-//     32*(warp%4)..+31, which is exactly its 32 pixels) and, at the end, the epilogue (tcgen05.ld -> bias ->
-//     LeakyReLU -> alpha/addend -> coalesced NCHW stores into the caller's channel slice); warp 8 = MMA issuer (one
-//     elected thread); warp 9 = weight loader.  Stage hand-off is mbarrier-only: a_full[s] (128 arrivals),
-//     b_full[s] (expect_tx), empty[s] (tcgen05.commit), acc_full (tcgen05.commit).
+//   * persistent CTAs, warp-specialised (roles and the measurements behind them are listed above the kernel and in
+//     DESIGN.md §4.2): 8 producer warps in two alternating groups, two MMA-issuing warps (one per 128-row half), a
+//     weight loader, four epilogue warps; hand-off is mbarrier-only (a_full / b_full / a_empty / b_empty via
+//     tcgen05.commit / acc_full / acc_empty).
 #include "common.cuh"
 
 namespace irr {
