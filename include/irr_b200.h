@@ -49,6 +49,8 @@ typedef struct CUstream_st* irr_stream_t;
 #define IRR_MATH_FP32_SIMT 0  /* CUDA-core FFMA implicit GEMM, fp32 accumulate */
 #define IRR_MATH_TC_3XTF32 1  /* tcgen05 kind::tf32, hi/lo split (3 MMAs) — fp32-grade accuracy */
 #define IRR_MATH_TC_TF32 2    /* tcgen05 kind::tf32 single pass — ~1e-3 relative, opt-in */
+#define IRR_MATH_TC_3XF16 3   /* tcgen05 kind::f16, hi/lo split (3 MMAs at twice the tf32 rate), activations staged
+                                 through shared memory by TMA — fp32-grade accuracy for |activation| < 65504 */
 
 int irr_abi_version(void);
 const char* irr_last_error(void);

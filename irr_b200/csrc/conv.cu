@@ -14,6 +14,11 @@ int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, co
             float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
             float alpha, int math, cudaStream_t st);
 bool tc_supported(int Cout, int Cin, int ks, int stride, int dil);
+size_t h16_packed_bytes(int Cout, int Cin, int ks);
+int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st);
+int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
+             float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
+             float alpha, cudaStream_t st);
 }  // namespace irr
 
 using namespace irr;
@@ -24,13 +29,15 @@ size_t irr_conv2d_packed_bytes(int Cout, int Cin, int ksize, int math) {
   if (Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3)) return 0;
   if (math == IRR_MATH_FP32_SIMT) return simt_packed_bytes(Cout, Cin, ksize);
   if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32) return tc_packed_bytes(Cout, Cin, ksize, math);
+  if (math == IRR_MATH_TC_3XF16) return Cout <= 256 ? h16_packed_bytes(Cout, Cin, ksize) : 0;
   return 0;
 }
 
 int irr_conv2d_math_supported(int Cout, int Cin, int ksize, int stride, int dilation, int math) {
   if (Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3) || stride < 1 || dilation < 1) return 0;
   if (math == IRR_MATH_FP32_SIMT) return 1;
-  if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32) return tc_supported(Cout, Cin, ksize, stride, dilation) ? 1 : 0;
+  if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32 || math == IRR_MATH_TC_3XF16)
+    return tc_supported(Cout, Cin, ksize, stride, dilation) ? 1 : 0;
   return 0;
 }
 
@@ -44,6 +51,10 @@ int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int C
   if (math == IRR_MATH_FP32_SIMT) return simt_pack(w_oihw, w_packed, Cout, Cin, ksize, as_stream(stream));
   if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32)
     return tc_pack(w_oihw, w_packed, Cout, Cin, ksize, math, as_stream(stream));
+  if (math == IRR_MATH_TC_3XF16) {
+    IRR_REQUIRE(Cout <= 256, fn, "Cout > 256 not supported by the tcgen05 path");
+    return h16_pack(w_oihw, w_packed, Cout, Cin, ksize, as_stream(stream));
+  }
   return fail_arg(fn, "unknown math mode");
 }
 
@@ -66,6 +77,14 @@ int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const f
     }
     return tc_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
                    leaky_slope, alpha, math, as_stream(stream));
+  }
+  if (math == IRR_MATH_TC_3XF16) {
+    if (!tc_supported(Cout, Cin, ksize, stride, dilation)) {
+      set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);
+      return IRR_E_UNSUPPORTED;
+    }
+    return h16_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
+                    leaky_slope, alpha, as_stream(stream));
   }
   return fail_arg(fn, "unknown math mode");
 }

@@ -1,0 +1,701 @@
+// conv() of models/pwc_modules.py:8-19 on the 5th-gen tensor cores, second generation of the kernel (math mode
+// IRR_MATH_TC_3XF16).  Same implicit GEMM as conv_tc.cu
+//
+//   D[2 x 128 px, N] (fp32, TMEM) += A[2 x 128 px, K] * B[N, K]^T,    K blocks = (32-channel chunk, tap)
+//
+// with the two things the first kernel's measurements asked for:
+//
+//   * 3xF16 instead of 3xTF32.  fp16 and tf32 carry the same 11 significant bits, but tcgen05 kind::f16 contracts
+//     K = 16 per dispatch where kind::tf32 contracts 8: the same three-term split
+//         v = hi + lo,  hi = f16(v),  lo = f16(v - hi)      (v - hi is exact in fp32)
+//         a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi            (fp32 accumulation in TMEM)
+//     runs at twice the tensor rate.  Dropped terms are 2^-22 relative, as in 3xTF32.  What fp16 lacks is exponent
+//     range, handled as follows: weights are pre-scaled per layer by a power of two that puts max|w| in [2^14, 2^15)
+//     (found on the device by the packer, undone exactly in the epilogue), so w_lo never goes subnormal in any way
+//     that matters; activations are not scaled: |a| < 65504 converts with saturation (never Inf), and where a_lo
+//     falls into fp16's subnormal range (|a| < 0.25) its ABSOLUTE error is bounded by 2^-25 = 3e-8 — below fp32's own
+//     rounding of the products this network forms.
+//   * Activations are staged through shared memory ONCE per (32-channel chunk), by TMA, instead of being gathered
+//     from global/L1 nine times (once per tap).  A 4-D tensor map over the NCHW channel-slice view delivers the
+//     chunk's rows with their halo — out-of-image rows/columns/channels arrive as zeros, which *is* the conv's zero
+//     padding and the ragged channel tail — and the nine taps are shifted conflict-free LDS views of that tile.
+//     The first kernel's producers were latency-bound on their global gathers (~1300 clk per K block, every layer
+//     with N <= 64 ran at the same 1.2 ms); here the producer chain is LDS -> split -> tcgen05.st.
+//     Work item = two 128-pixel halves, each RH rows x RW columns (RW = 128/RH a power of two chosen from the image
+//     width), stacked vertically so they share halo rows and every weight stage.
+//     Dilated layers (d >= 2) stage one tap ROW at a time (2*RH rows, three taps) — their halo would not fit.
+//     Layers the tensor map cannot describe (stride 2, W % 4 != 0, unaligned views) take the GATHER variant of the
+//     same kernel: identical pipeline, producers read global memory directly (as conv_tc.cu does).
+//
+// A operand in TMEM (tcgen05.st of packed f16x2: 16 columns hold 32 channels), B operand = pre-packed 128-byte-swizzled
+// K-major images [n][hi 32 ch | lo 32 ch] streamed by cp.async.bulk (or resident when the layer's images fit).
+// Roles: warps 0-7 A producers (two groups on alternate K blocks, each thread owns the same pixel of both halves),
+// 8-9 MMA issuers (one per half), 10 weight loader, 11 activation-tile loader (TMA), 12-15 epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace irr {
+
+constexpr int H_CK = 32;        // channels per K block (2 MMAs of K=16 per pass)
+constexpr int H_THREADS = 512;
+constexpr int H_TMEM_COLS = 512;
+constexpr int H_A_COL = 256;    // A ring: 4 stages x 2 halves x (hi 16 | lo 16) columns
+constexpr int H_SA = 4;
+constexpr int H_SX = 2;         // activation tile stages
+constexpr int H_SB_MAX = 16;    // weight ring depth limit
+constexpr int H_HDR = 128;      // packed-weights header bytes: {float max_abs, float inv_scale, float scale}
+constexpr size_t H_SMEM_MAX = 225 * 1024;
+
+struct HArgs {
+  const float* x; long long x_bs;
+  const uint8_t* wp;
+  const float* bias;
+  const float* addend; long long a_bs;
+  float* y; long long y_bs;
+  int B, Cin, H, W, Cout, Ho, Wo, stride, dil, pad;
+  int n_tile, n_tiles, cchunks, nkb, sb, resident;
+  unsigned b_smem_bytes, x_stage_bytes;
+  int rw_log2, rh, R, PW, padl, split, ytiles, xtiles, m_items, items;
+  long long M;
+  float slope, alpha;
+};
+
+struct HGeom {
+  int n_tiles, n_tile, cchunks, taps, nkb;
+  size_t img_bytes;
+};
+static inline int h_round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline HGeom h_geom(int Cout, int Cin, int ks) {
+  HGeom g;
+  g.n_tiles = (Cout + 127) / 128;
+  g.n_tile = h_round_up((Cout + g.n_tiles - 1) / g.n_tiles, 16);
+  g.cchunks = (Cin + H_CK - 1) / H_CK;
+  g.taps = ks * ks;
+  g.nkb = g.cchunks * g.taps;
+  g.img_bytes = (size_t)g.n_tile * 128;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void h_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void h_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ bool h_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void h_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void h_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void h_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem, f16x2 packed] * B[smem desc], fp32 accumulate
+__device__ __forceinline__ void h_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// {hi half = f16(b), lo half = f16(a)}: element k in the low half, k+1 in the high half.  satfinite: never Inf.
+__device__ __forceinline__ uint32_t h_pack(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void h_unpack(uint32_t r, float& a, float& b) {
+  asm("{ .reg .f16 x, y; mov.b32 {x, y}, %2; cvt.f32.f16 %0, x; cvt.f32.f16 %1, y; }" : "=f"(a), "=f"(b) : "r"(r));
+}
+__device__ __forceinline__ void h_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void h_tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (see conv_tc.cu make_b_desc).
+__device__ __forceinline__ uint64_t h_b_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ float h_zero_page[32];  // statically zero: source of out-of-image taps (gather variant)
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int KS, bool STAGED>
+__global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_constant__ CUtensorMap xmap, HArgs p) {
+  extern __shared__ __align__(1024) uint8_t h_smem[];
+  constexpr int T = KS * KS;
+  const int N = p.n_tile;
+  const int NBUF = N <= 64 ? 2 : 1;
+  const int acc_stride = N <= 64 ? 64 : 128;
+  const uint32_t img_bytes = (uint32_t)N * 128;
+  const int nkb = p.nkb;
+  const int SB = p.sb;
+  const bool resident = p.resident != 0;
+  const int m_items = p.m_items;
+  const int items = p.items;
+  const int TPS = STAGED ? (p.split ? KS : T) : 1;   // K blocks (taps) served by one activation stage
+  const int spi = STAGED ? nkb / TPS : 0;             // activation stages per work item
+
+  uint8_t* smem_b = h_smem;                            // 1024-aligned weight images
+  uint8_t* smem_x = h_smem + p.b_smem_bytes;           // activation tiles (128-aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_x + (STAGED ? H_SX * p.x_stage_bytes : 0));
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s, int h) { return bar0 + 8u * (s * 2 + h); };            // [0, 8)
+  auto a_empty = [&](int s) { return bar0 + 8u * (8 + s); };                      // [8, 12)
+  auto b_full = [&](int s) { return bar0 + 8u * (12 + s); };                      // [12, 28)
+  auto b_empty = [&](int s) { return bar0 + 8u * (28 + s); };                     // [28, 44)
+  auto acc_full = [&](int b) { return bar0 + 8u * (44 + b); };                    // [44, 46)
+  auto acc_empty = [&](int b) { return bar0 + 8u * (46 + b); };                   // [46, 48)
+  auto x_full = [&](int s) { return bar0 + 8u * (48 + s); };                      // [48, 50)
+  auto x_empty = [&](int s) { return bar0 + 8u * (50 + s); };                     // [50, 52)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 52);
+  float* bias_all = reinterpret_cast<float*>(bars + 54);  // n_tiles * N floats (<= 256)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < p.n_tiles * N; i += H_THREADS) bias_all[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < H_SA; ++s) {
+      mbar_init(a_full(s, 0), 4);  // the 4 producer warps of the group that owns this K block
+      mbar_init(a_full(s, 1), 4);
+      mbar_init(a_empty(s), 2);    // one tcgen05.commit per MMA issuer
+    }
+    for (int s = 0; s < H_SB_MAX; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 2);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 2);
+      mbar_init(acc_empty(b), 4);
+      mbar_init(x_full(b), 1);
+      mbar_init(x_empty(b), 8);    // all 8 producer warps release an activation stage
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(H_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  h_fence_before();
+  __syncthreads();
+  h_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const float inv_scale = __ldg(reinterpret_cast<const float*>(p.wp) + 1);
+  const uint8_t* wimg = p.wp + H_HDR;
+  const int HWo = p.Ho * p.Wo;
+  const int RW = 1 << p.rw_log2;
+  const int tiles_per_img = p.ytiles * p.xtiles;
+
+  // Work-item decode.  STAGED: item -> (n tile, image b, tile row ty, tile column tx); a half is RH rows x RW columns.
+  // GATHER: item -> (n tile, linear 256-pixel block).
+  auto item_origin = [&](int item, int& nt, int& b, int& y0, int& x0) {
+    nt = item / m_items;
+    int r = item - nt * m_items;
+    b = r / tiles_per_img;
+    r -= b * tiles_per_img;
+    const int ty = r / p.xtiles;
+    y0 = ty * (2 * p.rh);
+    x0 = (r - ty * p.xtiles) * RW;
+  };
+
+  if (warp < 8) {
+    // ======================= A producers =======================
+    const int grp = warp >> 2, q = warp & 3;
+    const int t = q * 32 + lane;                 // this thread's pixel index inside a half
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const size_t HW = (size_t)p.H * p.W;
+    // STAGED: float offsets of this thread's pixel (half 0 / half 1) inside an activation tile [32][R][PW]
+    const int rin = t >> p.rw_log2, xin = t & (RW - 1);
+    const int chp = p.R * p.PW;
+    const int off0 = rin * p.PW + xin, off1 = (p.rh + rin) * p.PW + xin;
+    int cur_item = -1;
+    bool m_ok[2] = {false, false};
+    int iy0[2] = {0, 0}, ix0[2] = {0, 0};
+    const float* xb[2] = {p.x, p.x};
+    int c = 0;
+    int gx = 0;          // activation stages seen so far (all producer warps count every stage)
+    bool waited = false;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++c) {
+        int tin = 0;
+        if (STAGED) {
+          const int sidx = kb / TPS;
+          tin = kb - sidx * TPS;
+          if (tin == 0) {  // a new activation stage starts here: release the previous one (every warp, every stage)
+            if (gx > 0) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(x_empty((gx - 1) % H_SX));
+            }
+            ++gx;
+            waited = false;
+          }
+        }
+        if ((c & 1) != grp) continue;
+        const int cc = kb / T, tap = kb - cc * T;
+        const int ky = tap / KS, kx = tap - ky * KS;
+        float v[2][H_CK];
+        if (STAGED) {
+          const int g = gx - 1;
+          if (!waited) {
+            mbar_wait(x_full(g % H_SX), (uint32_t)((g / H_SX) & 1));
+            waited = true;
+          }
+          const float* xs = reinterpret_cast<const float*>(smem_x + (size_t)(g % H_SX) * p.x_stage_bytes);
+          // tap (ky, kx) is the tile shifted by (ky*dil rows [0 in row-split mode], kx*dil columns); the tile starts
+          // padl >= pad columns left of the half (TMA needs a 16-byte aligned inner coordinate)
+          const int tapoff = (p.split ? 0 : ky * p.dil) * p.PW + (p.padl - p.pad) + kx * p.dil;
+          const float* s0 = xs + off0 + tapoff;
+          const float* s1 = xs + off1 + tapoff;
+#pragma unroll
+          for (int j = 0; j < H_CK; ++j) {
+            v[0][j] = s0[j * chp];
+            v[1][j] = s1[j * chp];
+          }
+        } else {
+          if (item != cur_item) {  // decode this thread's two output pixels (linear pixel blocks)
+            cur_item = item;
+            const int mt = item % m_items;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const long long mg = (long long)mt * 256 + h * 128 + t;
+              m_ok[h] = mg < p.M;
+              int ab = 0, aoy = 0, aox = 0;
+              if (m_ok[h]) {
+                ab = (int)(mg / HWo);
+                int rem = (int)(mg - (long long)ab * HWo);
+                aoy = rem / p.Wo;
+                aox = rem - aoy * p.Wo;
+              }
+              iy0[h] = aoy * p.stride - p.pad; ix0[h] = aox * p.stride - p.pad;
+              xb[h] = p.x + (size_t)ab * p.x_bs;
+            }
+          }
+          const int c0 = cc * H_CK;
+          const int nch = p.Cin - c0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int iy = iy0[h] + ky * p.dil, ix = ix0[h] + kx * p.dil;
+            const bool ok = m_ok[h] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            const float* src = ok ? xb[h] + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : h_zero_page;
+            const unsigned cstride = ok ? (unsigned)HW : 0u;
+            if (nch >= H_CK) {
+#pragma unroll
+              for (int j = 0; j < H_CK; ++j) v[h][j] = __ldg(src + (size_t)(j * cstride));
+            } else {
+#pragma unroll
+              for (int j = 0; j < H_CK; ++j) v[h][j] = (j < nch) ? __ldg(src + (size_t)(j * cstride)) : 0.f;
+            }
+          }
+        }
+        const int s = c % H_SA;
+        mbar_wait(a_empty(s), (uint32_t)(((c / H_SA) & 1) ^ 1));
+        h_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t a_addr = lane_addr + (uint32_t)(H_A_COL + (s * 2 + h) * 32);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v0 = v[h][2 * j], v1 = v[h][2 * j + 1];
+            hi[j] = h_pack(v0, v1);
+            float f0, f1;
+            h_unpack(hi[j], f0, f1);
+            lo[j] = h_pack(v0 - f0, v1 - f1);  // exact residuals, rounded to f16
+          }
+          h_tmem_st16(a_addr, hi);
+          h_tmem_st16(a_addr + 16, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        h_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(a_full(s, 0));
+          mbar_arrive(a_full(s, 1));
+        }
+      }
+    }
+  } else if (warp == 8 || warp == 9) {
+    // ======================= MMA issuers (one per half; warp converged, one elected lane issues) ==========
+    const int h = warp - 8;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
+    int c = 0, tcount = 0;
+    if (resident) mbar_wait(b_full(0), 0);
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
+      const int buf = NBUF == 2 ? (tcount & 1) : 0;
+      const int use = NBUF == 2 ? (tcount >> 1) : tcount;
+      mbar_wait(acc_empty(buf), (uint32_t)((use & 1) ^ 1));
+      const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 2 + h) * acc_stride);
+      for (int kb = 0; kb < nkb; ++kb, ++c) {
+        const int s = c % H_SA;
+        const uint32_t pha = (uint32_t)((c / H_SA) & 1);
+        const int sb = c % SB;
+        const int cc = kb / T;
+        const int nch = min(H_CK, p.Cin - cc * H_CK);
+        const int nk = (nch + 15) >> 4;   // K=16 steps that hold real channels (1 or 2)
+        uint32_t b_addr;
+        if (resident) {
+          b_addr = smem_u32(smem_b + (size_t)kb * img_bytes);
+        } else {
+          mbar_wait(b_full(sb), (uint32_t)((c / SB) & 1));
+          b_addr = smem_u32(smem_b + (size_t)sb * img_bytes);
+        }
+        const uint64_t bd = h_b_desc(b_addr);
+        const uint32_t a_hi = tmem_base + (uint32_t)(H_A_COL + (s * 2 + h) * 32);
+        mbar_wait(a_full(s, h), pha);
+        h_fence_after();
+        if (h_elect()) {
+#pragma unroll 2
+          for (int j = 0; j < nk; ++j) {
+            // K step j: A hi columns [8j, 8j+8), A lo columns [16+8j, ..); B hi bytes [32j, ..), B lo bytes [64+32j, ..)
+            const uint64_t b_hi = bd + (uint64_t)(2 * j), b_lo = bd + (uint64_t)(4 + 2 * j);
+            h_mma_ts(d_tmem, a_hi + 16 + 8 * j, b_hi, idesc, (kb | j) ? 1u : 0u);  // lo * hi
+            h_mma_ts(d_tmem, a_hi + 8 * j, b_lo, idesc, 1u);                       // hi * lo
+            h_mma_ts(d_tmem, a_hi + 8 * j, b_hi, idesc, 1u);                       // hi * hi
+          }
+          h_commit(a_empty(s));
+          if (!resident) h_commit(b_empty(sb));
+          if (kb == nkb - 1) h_commit(acc_full(buf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 10) {
+    // ======================= weight loader =======================
+    if (lane == 0) {
+      if (resident) {
+        mbar_expect_tx(b_full(0), img_bytes * (uint32_t)nkb);
+        for (int kb = 0; kb < nkb; ++kb)
+          h_bulk_g2s(smem_u32(smem_b + (size_t)kb * img_bytes), wimg + (size_t)kb * img_bytes, img_bytes, b_full(0));
+      } else {
+        int c = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+          const int nt = item / m_items;
+          for (int kb = 0; kb < nkb; ++kb, ++c) {
+            const int sb = c % SB;
+            mbar_wait(b_empty(sb), (uint32_t)(((c / SB) & 1) ^ 1));
+            mbar_expect_tx(b_full(sb), img_bytes);
+            h_bulk_g2s(smem_u32(smem_b + (size_t)sb * img_bytes), wimg + ((size_t)nt * nkb + kb) * img_bytes, img_bytes,
+                       b_full(sb));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 11) {
+    // ======================= activation-tile loader (TMA) =======================
+    if (STAGED) {
+      int g = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int nt, b, y0, x0;
+        item_origin(item, nt, b, y0, x0);
+        for (int sidx = 0; sidx < spi; ++sidx, ++g) {
+          const int sx = g % H_SX;
+          const int cc = p.split ? sidx / KS : sidx;
+          const int ky = p.split ? sidx - cc * KS : 0;
+          const int yy = p.split ? y0 + (ky - (KS / 2)) * p.dil : y0 - p.pad;
+          mbar_wait(x_empty(sx), (uint32_t)(((g / H_SX) & 1) ^ 1));
+          if (h_elect()) {
+            mbar_expect_tx(x_full(sx), p.x_stage_bytes);
+            h_tma_4d(smem_u32(smem_x + (size_t)sx * p.x_stage_bytes), &xmap, x0 - p.padl, yy, cc * H_CK, b, x_full(sx));
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 12) {
+    // ======================= epilogue: TMEM -> 1/scale, bias, LeakyReLU, alpha, addend -> NCHW slice ==============
+    const int q = warp & 3;
+    const int t = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int rin = t >> p.rw_log2, xin = t & (RW - 1);
+    int tcount = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
+      const int buf = NBUF == 2 ? (tcount & 1) : 0;
+      const int use = NBUF == 2 ? (tcount >> 1) : tcount;
+      int nt, ib, y0, x0;
+      item_origin(item, nt, ib, y0, x0);
+      const int mt = item - nt * m_items;
+      const float* bias_s = bias_all + nt * N;
+      mbar_wait(acc_full(buf), (uint32_t)(use & 1));
+      h_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        bool m_ok;
+        int ob = 0, opix = 0;
+        if (STAGED) {
+          const int oy = y0 + h * p.rh + rin, ox = x0 + xin;
+          m_ok = oy < p.Ho && ox < p.Wo;
+          ob = ib;
+          opix = m_ok ? oy * p.Wo + ox : 0;
+        } else {
+          const long long mg = (long long)mt * 256 + h * 128 + t;
+          m_ok = mg < p.M;
+          if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
+        }
+        const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
+        const float* ap = p.addend ? p.addend + (size_t)ob * p.a_bs + opix : nullptr;
+        float* yp = p.y + (size_t)ob * p.y_bs + opix;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          const int nb = nt * N + c0;
+          float add[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            add[j] = (ap != nullptr && m_ok && nb + j < p.Cout) ? __ldg(ap + (size_t)(nb + j) * HWo) : 0.f;
+          uint32_t r[16];
+          h_tmem_ld16(acc_addr + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (m_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (nb + j < p.Cout) {
+                float val = fmaf(__uint_as_float(r[j]), inv_scale, bias_s[c0 + j]);
+                val = fmaf(leaky(val, p.slope), p.alpha, add[j]);
+                yp[(size_t)(nb + j) * HWo] = val;
+              }
+            }
+          }
+        }
+      }
+      h_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+  }
+
+  h_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    h_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packer
+// Pass 1: max|w| of the layer -> header {max_abs, inv_scale, scale}, scale = 2^(14 - floor(log2(max))).
+__global__ void h16_scale_kernel(const float* __restrict__ w, float* __restrict__ hdr, long long n) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(w + i)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) e = 14 - ilogbf(m);
+      e = max(-100, min(100, e));
+      hdr[0] = m;
+      hdr[1] = ldexpf(1.0f, -e);
+      hdr[2] = ldexpf(1.0f, e);
+    }
+  }
+}
+// Pass 2: one thread per (n tile, k block, row n, channel j): OIHW -> [n][hi 32 ch | lo 32 ch] f16, 128-byte rows,
+// 16-byte chunks XOR (n % 8)  [Swizzle<3,4,3>].
+__global__ void h16_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int ks,
+                                int n_tile, int cchunks, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float scale = reinterpret_cast<const float*>(out)[2];
+  const int T = ks * ks;
+  int j = (int)(i % H_CK);
+  long long r = i / H_CK;
+  int n = (int)(r % n_tile); r /= n_tile;
+  int kb = (int)(r % (cchunks * T));
+  int nt = (int)(r / (cchunks * T));
+  int cc = kb / T, tap = kb - cc * T;
+  int c = cc * H_CK + j, ng = nt * n_tile + n;
+  float v = 0.f;
+  if (c < Cin && ng < Cout) v = __ldg(w + ((size_t)ng * Cin + c) * T + tap) * scale;  // power of two: exact
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  uint8_t* img = out + H_HDR + ((size_t)nt * cchunks * T + kb) * ((size_t)n_tile * 128);
+  const int bhi = j * 2, blo = 64 + j * 2;  // byte offsets inside the logical 128-byte row
+  auto sw = [&](int byte) { return (size_t)n * 128 + (size_t)((((byte >> 4) ^ (n & 7)) << 4) | (byte & 15)); };
+  *reinterpret_cast<__half*>(img + sw(bhi)) = hi;
+  *reinterpret_cast<__half*>(img + sw(blo)) = lo;
+}
+
+size_t h16_packed_bytes(int Cout, int Cin, int ks) {
+  HGeom g = h_geom(Cout, Cin, ks);
+  return (size_t)H_HDR + (size_t)g.n_tiles * g.nkb * g.img_bytes;
+}
+
+int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st) {
+  HGeom g = h_geom(Cout, Cin, ks);
+  h16_scale_kernel<<<1, 1024, 0, st>>>(w, (float*)out, (long long)Cout * Cin * ks * ks);
+  long long total = (long long)g.n_tiles * g.nkb * g.n_tile * H_CK;
+  h16_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, (uint8_t*)out, Cout, Cin, ks, g.n_tile, g.cchunks,
+                                                                  total);
+  return check_launch("irr_conv2d_pack_weights");
+}
+
+// ------------------------------------------------------------------------------------------------ host launcher
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <int KS, bool STAGED>
+static int launch_h16(const CUtensorMap& map, const HArgs& a, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_h16_kernel<KS, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_smem = smem;
+  }
+  int grid = a.items < sm_count() ? a.items : sm_count();
+  conv_h16_kernel<KS, STAGED><<<grid, H_THREADS, smem, st>>>(map, a);
+  return check_launch("irr_conv2d_fwd");
+}
+
+// force_gather: testing hook (IRR_CONV_GATHER=1) so both producer variants can be exercised on any shape.
+static bool force_gather() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRR_CONV_GATHER");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
+             float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
+             float alpha, cudaStream_t st) {
+  HGeom g = h_geom(Cout, Cin, ks);
+  HArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.x_bs = x_bs; a.wp = (const uint8_t*)w; a.bias = bias; a.addend = addend; a.a_bs = a_bs; a.y = y; a.y_bs = y_bs;
+  a.B = B; a.Cin = Cin; a.H = H; a.W = W; a.Cout = Cout; a.stride = stride; a.dil = dil;
+  a.pad = ((ks - 1) * dil) / 2;
+  a.Ho = (H + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
+  a.Wo = (W + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
+  a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb;
+  a.M = (long long)B * a.Ho * a.Wo;
+  a.slope = slope; a.alpha = alpha;
+  const size_t misc = 54 * 8 + 256 * 4 + 64;
+  const size_t total_b = (size_t)g.nkb * g.img_bytes;
+
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  EncodeTiledFn enc = encode_tiled();
+  bool staged = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
+                (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
+  if (staged) {
+    // half = RH rows x RW columns, RW = smallest power of two >= W, clamped to [16, 128]
+    int rwl = 4;
+    while ((1 << rwl) < W && rwl < 7) ++rwl;
+    const int RW = 1 << rwl, RH = 128 / RW;
+    a.rw_log2 = rwl; a.rh = RH;
+    a.split = (ks == 3 && dil > 1) ? 1 : 0;
+    a.R = a.split ? 2 * RH : 2 * RH + 2 * a.pad;
+    a.padl = h_round_up(a.pad, 4);  // the tile's first column must be 16-byte aligned in global memory
+    a.PW = h_round_up(RW + a.padl + a.pad, 4);
+    a.x_stage_bytes = (unsigned)h_round_up(H_CK * a.R * a.PW * 4, 128);
+    a.ytiles = (a.Ho + 2 * RH - 1) / (2 * RH);
+    a.xtiles = (a.Wo + RW - 1) / RW;
+    a.m_items = B * a.ytiles * a.xtiles;
+    if (a.PW > 256 || a.R > 256 || (size_t)H_SX * a.x_stage_bytes + 2 * g.img_bytes + misc > H_SMEM_MAX) staged = false;
+  }
+  if (staged) {
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)x_bs * 4};
+    cuuint32_t box[4] = {(cuuint32_t)a.PW, (cuuint32_t)a.R, (cuuint32_t)H_CK, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) staged = false;  // e.g. a batch stride the tensor map cannot express -> gather variant
+  }
+  size_t x_bytes = 0;
+  if (staged) {
+    x_bytes = (size_t)H_SX * a.x_stage_bytes;
+  } else {
+    a.rw_log2 = 7; a.rh = 1; a.R = 0; a.PW = 0; a.padl = 0; a.split = 0; a.x_stage_bytes = 0;
+    a.ytiles = 1; a.xtiles = 1;
+    a.m_items = (int)((a.M + 255) / 256);
+  }
+  a.items = a.m_items * g.n_tiles;
+  const size_t room = H_SMEM_MAX - x_bytes - misc;
+  a.resident = (g.n_tiles == 1 && total_b <= room) ? 1 : 0;
+  if (a.resident) {
+    a.sb = 1;
+    a.b_smem_bytes = (unsigned)total_b;
+  } else {
+    size_t ring = 64 * 1024;
+    if (ring > room) ring = room;
+    int sb = (int)(ring / g.img_bytes);
+    if (sb > H_SB_MAX) sb = H_SB_MAX;
+    if (sb < 2) {
+      set_error("irr_conv2d_fwd: shared memory budget exceeded (n_tile=%d)", g.n_tile);
+      return IRR_E_UNSUPPORTED;
+    }
+    a.sb = sb;
+    a.b_smem_bytes = (unsigned)((size_t)sb * g.img_bytes);
+  }
+  const size_t smem = (size_t)a.b_smem_bytes + x_bytes + misc;
+  if (staged) return ks == 1 ? launch_h16<1, true>(map, a, smem, st) : launch_h16<3, true>(map, a, smem, st);
+  return ks == 1 ? launch_h16<1, false>(map, a, smem, st) : launch_h16<3, false>(map, a, smem, st);
+}
+
+}  // namespace irr

@@ -16,6 +16,7 @@ from . import _lib
 MATH_FP32_SIMT = 0
 MATH_TC_3XTF32 = 1
 MATH_TC_TF32 = 2
+MATH_TC_3XF16 = 3
 
 GRID_TRUE_DIV = 0   # reference-on-CPU arithmetic (IEEE divisions)
 GRID_RECIP_MUL = 1  # torch-CUDA `tensor / python_scalar` arithmetic (a * (1/b))

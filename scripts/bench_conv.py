@@ -12,7 +12,7 @@ SHAPES = [  # (B, Cin, H, W, Cout, k, stride, dil)
     (16, 32, 436, 1024, 1, 3, 1, 1), (16, 64, 109, 256, 32, 3, 1, 1), (16, 3, 436, 1024, 16, 3, 2, 1),
     (16, 16, 218, 512, 16, 3, 1, 1), (16, 128, 55, 128, 128, 3, 1, 1), (16, 196, 7, 16, 32, 1, 1, 1),
 ]
-MODES = {"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32, "tf32": ops.MATH_TC_TF32}
+MODES = {"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32, "tf32": ops.MATH_TC_TF32, "3xf16": ops.MATH_TC_3XF16}
 modes = [m for m in sys.argv[1:] if m in MODES] or ["3xtf32"]
 only = os.environ.get("IRR_CONV_ONLY")
 dev = torch.device("cuda:0")
@@ -30,7 +30,7 @@ for i, (B, Cin, H, W, Cout, k, s, d) in enumerate(SHAPES):
     ref = None
     for m in modes:
         math = MODES[m]
-        if not ops.tc_supported(Cout, Cin, k, s, d, math) and math != 0:
+        if math != 0 and not ops.tc_supported(Cout, Cin, k, s, d, math):
             line += f"{m}: n/a  "
             continue
         pk = ops.pack_weights(w, math)

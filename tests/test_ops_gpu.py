@@ -264,6 +264,51 @@ TC_CASES = [
 ]
 
 
+# extra shapes for the TMA-staged 3xF16 kernel: every half geometry (RW = 16..128), row-split dilations, ragged
+# tiles in x and y, partial last row pair, wide rows (several x tiles), >1 item per CTA with streamed weights
+H16_CASES = TC_CASES + [
+    (1, 64, 109, 256, 64, 3, 1, 1), (2, 128, 30, 256, 128, 3, 1, 2), (1, 40, 20, 512, 32, 3, 1, 1),
+    (1, 32, 12, 16, 16, 3, 1, 1), (1, 48, 9, 8, 32, 3, 1, 1), (2, 128, 28, 64, 128, 3, 1, 4), (1, 96, 33, 132, 96, 3, 1, 2),
+    (1, 33, 7, 260, 48, 1, 1, 1), (6, 243, 55, 128, 128, 3, 1, 1), (3, 64, 50, 1024, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", H16_CASES)
+def test_conv2d_3xf16_vs_torch_cpu(cuda, case):
+    """tcgen05 kind::f16 hi/lo-split conv (TMA-staged and gather variants) against an fp64 CPU conv."""
+    from irr_b200 import ops
+    B, Cin, H, W, Cout, k, s, d = case
+    assert ops.tc_supported(Cout, Cin, k, s, d, ops.MATH_TC_3XF16)
+    torch.manual_seed(41)
+    x = torch.randn(B, Cin, H, W)
+    x[0, 0, 0, :4] = torch.tensor([3.0e-6, -2.0e-5, 900.0, -4.0e3])[: min(4, W)]   # fp16-subnormal / large magnitudes
+    w = torch.from_numpy(rs(42, (Cout, Cin, k, k))) * float(np.sqrt(2.0 / (Cin * k * k)))
+    b = torch.from_numpy(rs(43, (Cout,))) * 0.1
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s, padding=((k - 1) * d) // 2, dilation=d), 0.1)
+    packed = ops.pack_weights(w.to(cuda), ops.MATH_TC_3XF16)
+    got = ops.conv2d(x.to(cuda), packed, b.to(cuda), Cout, k, s, d, slope=0.1, math=ops.MATH_TC_3XF16)
+    err = (got.cpu().double() - ref).abs().max().item()
+    refmax = ref.abs().max().item()
+    print(f"[h16] {case}: max-abs {err:.3e} (|ref|max {refmax:.2f})")
+    assert err <= 5e-5 * max(2.0, refmax)
+
+
+def test_conv2d_3xf16_slices_addend(cuda):
+    from irr_b200 import ops
+    B, Ct, H, W = 2, 100, 20, 36
+    buf = torch.from_numpy(rs(51, (B, Ct, H, W))).to(cuda)
+    w = torch.from_numpy(rs(52, (48, 72, 3, 3))) * 0.05
+    b = torch.from_numpy(rs(53, (48,))) * 0.1
+    add = torch.from_numpy(rs(54, (B, 48, H, W))).to(cuda)
+    ref = add.cpu() + 0.1 * torch.nn.functional.conv2d(buf[:, 28:100].cpu(), w, b, padding=1)
+    out = torch.zeros((B, 60, H, W), device=cuda)
+    ops.conv2d(buf[:, 28:100], ops.pack_weights(w.to(cuda), ops.MATH_TC_3XF16), b.to(cuda), 48, 3, slope=1.0,
+               out=out[:, 5:53], addend=add, alpha=0.1, math=ops.MATH_TC_3XF16)
+    assert (out[:, 5:53].cpu() - ref).abs().max().item() <= 1e-4
+    assert (out[:, :5] == 0).all() and (out[:, 53:] == 0).all()
+
+
 @pytest.mark.parametrize("case", TC_CASES)
 @pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
 def test_conv2d_tcgen05_vs_torch_cpu(cuda, case, mode):
