@@ -158,9 +158,16 @@ __device__ __forceinline__ uint64_t h_b_desc(uint32_t smem_addr) {
 }
 
 __device__ float h_zero_page[32];  // statically zero: source of out-of-image taps (gather variant)
+// Debug only (scripts/h16_counters.py): when set, the CTR instantiation runs and CTA 0 accumulates per-role cycle
+// counts here.  The production instantiation (CTR = false) carries no counter code.
+__device__ long long* h_ctr_ptr = nullptr;
+static long long* h_ctr_host = nullptr;
+#define H_T0() long long t_ = 0; if (CTR) t_ = clock64()
+#define H_RST() do { if (CTR) t_ = clock64(); } while (0)
+#define H_ACC(i) do { if (CTR) { long long n_ = clock64(); cacc[i] += n_ - t_; t_ = n_; } } while (0)
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int KS, bool STAGED>
+template <int KS, bool STAGED, bool CTR>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_constant__ CUtensorMap xmap, HArgs p) {
   extern __shared__ __align__(1024) uint8_t h_smem[];
   constexpr int T = KS * KS;
@@ -189,9 +196,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
   auto x_full = [&](int s) { return bar0 + 8u * (48 + s); };                      // [48, 50)
   auto x_empty = [&](int s) { return bar0 + 8u * (50 + s); };                     // [50, 52)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 52);
-  float* bias_all = reinterpret_cast<float*>(bars + 54);  // n_tiles * N floats (<= 256)
+  float* bias_all = reinterpret_cast<float*>(bars + 56);  // n_tiles * N floats (<= 256), 16-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* ctr = (CTR && blockIdx.x == 0) ? h_ctr_ptr : nullptr;
+  long long cacc[6] = {0, 0, 0, 0, 0, 0};
+  (void)ctr; (void)cacc;
 
   for (int i = tid; i < p.n_tiles * N; i += H_THREADS) bias_all[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   if (tid == 0) {
@@ -246,52 +256,77 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
     const int t = q * 32 + lane;                 // this thread's pixel index inside a half
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const size_t HW = (size_t)p.H * p.W;
-    // STAGED: float offsets of this thread's pixel (half 0 / half 1) inside an activation tile [32][R][PW]
+    // STAGED: word offsets of this thread's pixel (half 0 / half 1) inside an activation tile [32][R][PW]
     const int rin = t >> p.rw_log2, xin = t & (RW - 1);
-    const int chp = p.R * p.PW;
+    const int chp = p.R * p.PW;                  // plane pitch = positions per tile
     const int off0 = rin * p.PW + xin, off1 = (p.rh + rin) * p.PW + xin;
     int cur_item = -1;
     bool m_ok[2] = {false, false};
     int iy0[2] = {0, 0}, ix0[2] = {0, 0};
     const float* xb[2] = {p.x, p.x};
     int c = 0;
-    int gx = 0;          // activation stages seen so far (all producer warps count every stage)
-    bool waited = false;
+    int gx = 0;          // activation stages seen so far (all producer warps walk every stage)
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int tin = 0, tap = 0, cc = 0;
       for (int kb = 0; kb < nkb; ++kb, ++c) {
-        int tin = 0;
-        if (STAGED) {
-          const int sidx = kb / TPS;
-          tin = kb - sidx * TPS;
-          if (tin == 0) {  // a new activation stage starts here: release the previous one (every warp, every stage)
-            if (gx > 0) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(x_empty((gx - 1) % H_SX));
-            }
-            ++gx;
-            waited = false;
+        const int ky = tap / KS, kx = tap - ky * KS;
+        const int my_cc = cc, my_tin = tin;
+        if (++tap == T) { tap = 0; ++cc; }
+        if (++tin == TPS) tin = 0;
+        H_T0();
+        if (STAGED && my_tin == 0) {
+          // A new activation stage starts at this K block.  Every producer warp (both groups): release the previous
+          // stage, wait for the TMA tile, and convert its share of the tile IN PLACE from fp32 planes to packed
+          // f16x2 planes: plane 2k <- {hi(ch 2k), hi(ch 2k+1)}, plane 2k+1 <- {lo(ch 2k), lo(ch 2k+1)}.  Each input
+          // element is split once per chunk instead of once per tap; the taps below only copy words to TMEM.
+          if (gx > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our generic accesses before the next TMA write
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_empty((gx - 1) % H_SX));
           }
+          const int g = gx++;
+          mbar_wait(x_full(g % H_SX), (uint32_t)((g / H_SX) & 1));
+          H_ACC(0);
+          float* xs = reinterpret_cast<float*>(smem_x + (size_t)(g % H_SX) * p.x_stage_bytes);
+          // units of (position, group of 4 channel pairs), consecutive threads on consecutive positions
+          int pos = tid, pg = 0;
+          while (pos >= chp) { pos -= chp; ++pg; }
+          while (pg < 4) {
+            float* base = xs + (size_t)(pg * 8) * chp + pos;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = base[j * chp];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t hi = h_pack(v[2 * k], v[2 * k + 1]);
+              float f0, f1;
+              h_unpack(hi, f0, f1);
+              const uint32_t lo = h_pack(v[2 * k] - f0, v[2 * k + 1] - f1);  // exact residuals, rounded to f16
+              base[(2 * k) * chp] = __uint_as_float(hi);
+              base[(2 * k + 1) * chp] = __uint_as_float(lo);
+            }
+            pos += 256;
+            while (pos >= chp) { pos -= chp; ++pg; }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps: tile fully converted
+          H_ACC(1);
         }
         if ((c & 1) != grp) continue;
-        const int cc = kb / T, tap = kb - cc * T;
-        const int ky = tap / KS, kx = tap - ky * KS;
-        float v[2][H_CK];
+        uint32_t hi[2][16], lo[2][16];
         if (STAGED) {
           const int g = gx - 1;
-          if (!waited) {
-            mbar_wait(x_full(g % H_SX), (uint32_t)((g / H_SX) & 1));
-            waited = true;
-          }
-          const float* xs = reinterpret_cast<const float*>(smem_x + (size_t)(g % H_SX) * p.x_stage_bytes);
+          const uint32_t* xs = reinterpret_cast<const uint32_t*>(smem_x + (size_t)(g % H_SX) * p.x_stage_bytes);
           // tap (ky, kx) is the tile shifted by (ky*dil rows [0 in row-split mode], kx*dil columns); the tile starts
           // padl >= pad columns left of the half (TMA needs a 16-byte aligned inner coordinate)
           const int tapoff = (p.split ? 0 : ky * p.dil) * p.PW + (p.padl - p.pad) + kx * p.dil;
-          const float* s0 = xs + off0 + tapoff;
-          const float* s1 = xs + off1 + tapoff;
+          const uint32_t* s0 = xs + off0 + tapoff;
+          const uint32_t* s1 = xs + off1 + tapoff;
 #pragma unroll
-          for (int j = 0; j < H_CK; ++j) {
-            v[0][j] = s0[j * chp];
-            v[1][j] = s1[j * chp];
+          for (int k = 0; k < 16; ++k) {
+            hi[0][k] = s0[(2 * k) * chp];
+            lo[0][k] = s0[(2 * k + 1) * chp];
+            hi[1][k] = s1[(2 * k) * chp];
+            lo[1][k] = s1[(2 * k + 1) * chp];
           }
         } else {
           if (item != cur_item) {  // decode this thread's two output pixels (linear pixel blocks)
@@ -312,7 +347,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
               xb[h] = p.x + (size_t)ab * p.x_bs;
             }
           }
-          const int c0 = cc * H_CK;
+          const int c0 = my_cc * H_CK;
           const int nch = p.Cin - c0;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -320,32 +355,33 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
             const bool ok = m_ok[h] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
             const float* src = ok ? xb[h] + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : h_zero_page;
             const unsigned cstride = ok ? (unsigned)HW : 0u;
+            float v[H_CK];
             if (nch >= H_CK) {
 #pragma unroll
-              for (int j = 0; j < H_CK; ++j) v[h][j] = __ldg(src + (size_t)(j * cstride));
+              for (int j = 0; j < H_CK; ++j) v[j] = __ldg(src + (size_t)(j * cstride));
             } else {
 #pragma unroll
-              for (int j = 0; j < H_CK; ++j) v[h][j] = (j < nch) ? __ldg(src + (size_t)(j * cstride)) : 0.f;
+              for (int j = 0; j < H_CK; ++j) v[j] = (j < nch) ? __ldg(src + (size_t)(j * cstride)) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              hi[h][k] = h_pack(v[2 * k], v[2 * k + 1]);
+              float f0, f1;
+              h_unpack(hi[h][k], f0, f1);
+              lo[h][k] = h_pack(v[2 * k] - f0, v[2 * k + 1] - f1);
             }
           }
         }
         const int s = c % H_SA;
+        H_ACC(2);
         mbar_wait(a_empty(s), (uint32_t)(((c / H_SA) & 1) ^ 1));
         h_fence_after();
+        H_ACC(3);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint32_t a_addr = lane_addr + (uint32_t)(H_A_COL + (s * 2 + h) * 32);
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v0 = v[h][2 * j], v1 = v[h][2 * j + 1];
-            hi[j] = h_pack(v0, v1);
-            float f0, f1;
-            h_unpack(hi[j], f0, f1);
-            lo[j] = h_pack(v0 - f0, v1 - f1);  // exact residuals, rounded to f16
-          }
-          h_tmem_st16(a_addr, hi);
-          h_tmem_st16(a_addr + 16, lo);
+          h_tmem_st16(a_addr, hi[h]);
+          h_tmem_st16(a_addr + 16, lo[h]);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         h_fence_before();
@@ -354,53 +390,68 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           mbar_arrive(a_full(s, 0));
           mbar_arrive(a_full(s, 1));
         }
+        H_ACC(4);
+        if (CTR) cacc[5] += 1;
       }
     }
+    if (CTR && ctr && warp == 0 && lane == 0)
+      for (int i = 0; i < 6; ++i) ctr[i] = cacc[i];
   } else if (warp == 8 || warp == 9) {
     // ======================= MMA issuers (one per half; warp converged, one elected lane issues) ==========
     const int h = warp - 8;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
-    int c = 0, tcount = 0;
+    const int nk_last = (p.Cin - (p.cchunks - 1) * H_CK + 15) >> 4;  // K=16 steps with real channels in the last chunk
+    int s = 0, sb = 0, tcount = 0;
+    uint32_t a_par = 0, b_par = 0;
     if (resident) mbar_wait(b_full(0), 0);
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
       const int buf = NBUF == 2 ? (tcount & 1) : 0;
       const int use = NBUF == 2 ? (tcount >> 1) : tcount;
+      H_T0();
       mbar_wait(acc_empty(buf), (uint32_t)((use & 1) ^ 1));
+      H_ACC(0);
       const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 2 + h) * acc_stride);
-      for (int kb = 0; kb < nkb; ++kb, ++c) {
-        const int s = c % H_SA;
-        const uint32_t pha = (uint32_t)((c / H_SA) & 1);
-        const int sb = c % SB;
-        const int cc = kb / T;
-        const int nch = min(H_CK, p.Cin - cc * H_CK);
-        const int nk = (nch + 15) >> 4;   // K=16 steps that hold real channels (1 or 2)
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const bool two = cc < p.cchunks - 1 || nk_last == 2;
         uint32_t b_addr;
+        H_RST();
         if (resident) {
-          b_addr = smem_u32(smem_b + (size_t)kb * img_bytes);
+          b_addr = smem_u32(smem_b) + (uint32_t)kb * img_bytes;
         } else {
-          mbar_wait(b_full(sb), (uint32_t)((c / SB) & 1));
-          b_addr = smem_u32(smem_b + (size_t)sb * img_bytes);
+          mbar_wait(b_full(sb), b_par);
+          b_addr = smem_u32(smem_b) + (uint32_t)sb * img_bytes;
         }
+        H_ACC(1);
         const uint64_t bd = h_b_desc(b_addr);
         const uint32_t a_hi = tmem_base + (uint32_t)(H_A_COL + (s * 2 + h) * 32);
-        mbar_wait(a_full(s, h), pha);
+        mbar_wait(a_full(s, h), a_par);
         h_fence_after();
+        H_ACC(2);
         if (h_elect()) {
-#pragma unroll 2
-          for (int j = 0; j < nk; ++j) {
-            // K step j: A hi columns [8j, 8j+8), A lo columns [16+8j, ..); B hi bytes [32j, ..), B lo bytes [64+32j, ..)
-            const uint64_t b_hi = bd + (uint64_t)(2 * j), b_lo = bd + (uint64_t)(4 + 2 * j);
-            h_mma_ts(d_tmem, a_hi + 16 + 8 * j, b_hi, idesc, (kb | j) ? 1u : 0u);  // lo * hi
-            h_mma_ts(d_tmem, a_hi + 8 * j, b_lo, idesc, 1u);                       // hi * lo
-            h_mma_ts(d_tmem, a_hi + 8 * j, b_hi, idesc, 1u);                       // hi * hi
+          // K step j: A hi columns [8j, 8j+8), A lo columns [16+8j, ..); B hi bytes [32j, ..), B lo bytes [64+32j, ..)
+          h_mma_ts(d_tmem, a_hi + 16, bd, idesc, kb ? 1u : 0u);  // lo * hi
+          h_mma_ts(d_tmem, a_hi, bd + 4, idesc, 1u);             // hi * lo
+          h_mma_ts(d_tmem, a_hi, bd, idesc, 1u);                 // hi * hi
+          if (two) {
+            h_mma_ts(d_tmem, a_hi + 24, bd + 2, idesc, 1u);
+            h_mma_ts(d_tmem, a_hi + 8, bd + 6, idesc, 1u);
+            h_mma_ts(d_tmem, a_hi + 8, bd + 2, idesc, 1u);
           }
           h_commit(a_empty(s));
           if (!resident) h_commit(b_empty(sb));
           if (kb == nkb - 1) h_commit(acc_full(buf));
         }
         __syncwarp();
+        if (++s == H_SA) { s = 0; a_par ^= 1; }
+        if (++sb == SB) { sb = 0; b_par ^= 1; }
+        if (++tap == T) { tap = 0; ++cc; }
+        H_ACC(3);
+        if (CTR) cacc[5] += 1;
       }
     }
+    if (CTR && ctr && warp == 8 && lane == 0)
+      for (int i = 0; i < 6; ++i) ctr[8 + i] = cacc[i];
   } else if (warp == 10) {
     // ======================= weight loader =======================
     if (lane == 0) {
@@ -409,15 +460,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
         for (int kb = 0; kb < nkb; ++kb)
           h_bulk_g2s(smem_u32(smem_b + (size_t)kb * img_bytes), wimg + (size_t)kb * img_bytes, img_bytes, b_full(0));
       } else {
-        int c = 0;
+        int sb = 0;
+        uint32_t par = 1;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
           const int nt = item / m_items;
-          for (int kb = 0; kb < nkb; ++kb, ++c) {
-            const int sb = c % SB;
-            mbar_wait(b_empty(sb), (uint32_t)(((c / SB) & 1) ^ 1));
+          const uint8_t* src = wimg + (size_t)nt * nkb * img_bytes;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(b_empty(sb), par);
             mbar_expect_tx(b_full(sb), img_bytes);
-            h_bulk_g2s(smem_u32(smem_b + (size_t)sb * img_bytes), wimg + ((size_t)nt * nkb + kb) * img_bytes, img_bytes,
-                       b_full(sb));
+            h_bulk_g2s(smem_u32(smem_b) + (uint32_t)sb * img_bytes, src + (size_t)kb * img_bytes, img_bytes, b_full(sb));
+            if (++sb == SB) { sb = 0; par ^= 1; }
           }
         }
       }
@@ -435,7 +487,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           const int cc = p.split ? sidx / KS : sidx;
           const int ky = p.split ? sidx - cc * KS : 0;
           const int yy = p.split ? y0 + (ky - (KS / 2)) * p.dil : y0 - p.pad;
+          H_T0();
           mbar_wait(x_empty(sx), (uint32_t)(((g / H_SX) & 1) ^ 1));
+          H_ACC(0);
+          if (CTR) cacc[5] += 1;
           if (h_elect()) {
             mbar_expect_tx(x_full(sx), p.x_stage_bytes);
             h_tma_4d(smem_u32(smem_x + (size_t)sx * p.x_stage_bytes), &xmap, x0 - p.padl, yy, cc * H_CK, b, x_full(sx));
@@ -443,6 +498,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           __syncwarp();
         }
       }
+      if (CTR && ctr && lane == 0) { ctr[16] = cacc[0]; ctr[17] = cacc[5]; }
     }
     __syncwarp();
   } else if (warp >= 12) {
@@ -451,6 +507,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
     const int t = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int rin = t >> p.rw_log2, xin = t & (RW - 1);
+    const float slope = p.slope, alpha = p.alpha;
     int tcount = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
       const int buf = NBUF == 2 ? (tcount & 1) : 0;
@@ -459,8 +516,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
       item_origin(item, nt, ib, y0, x0);
       const int mt = item - nt * m_items;
       const float* bias_s = bias_all + nt * N;
+      H_T0();
       mbar_wait(acc_full(buf), (uint32_t)(use & 1));
       h_fence_after();
+      H_ACC(0);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         bool m_ok;
@@ -476,32 +535,57 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
         }
         const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
-        const float* ap = p.addend ? p.addend + (size_t)ob * p.a_bs + opix : nullptr;
+        const bool has_add = p.addend != nullptr;
+        const float* ap = has_add ? p.addend + (size_t)ob * p.a_bs + opix : p.y;
         float* yp = p.y + (size_t)ob * p.y_bs + opix;
+#pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 16) {
           const int nb = nt * N + c0;
+          const int nvalid = min(16, p.Cout - nb);  // warp-uniform; < 16 only in the layer's last channel group
+          if (nvalid <= 0) break;
+          // residual / skip operand: 16 independent loads in flight before the accumulator is touched
           float add[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            add[j] = (ap != nullptr && m_ok && nb + j < p.Cout) ? __ldg(ap + (size_t)(nb + j) * HWo) : 0.f;
+            add[j] = (has_add && m_ok && j < nvalid) ? __ldg(ap + (size_t)(nb + j) * HWo) : 0.f;
           uint32_t r[16];
+          H_ACC(1);
           h_tmem_ld16(acc_addr + (uint32_t)c0, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (m_ok) {
+          float bs[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (nb + j < p.Cout) {
-                float val = fmaf(__uint_as_float(r[j]), inv_scale, bias_s[c0 + j]);
-                val = fmaf(leaky(val, p.slope), p.alpha, add[j]);
-                yp[(size_t)(nb + j) * HWo] = val;
-              }
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+            bs[4 * j] = b4.x; bs[4 * j + 1] = b4.y; bs[4 * j + 2] = b4.z; bs[4 * j + 3] = b4.w;
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          H_ACC(2);
+          float val[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaf(__uint_as_float(r[j]), inv_scale, bs[j]);
+            val[j] = fmaf(leaky(a, slope), alpha, add[j]);
+          }
+          if (m_ok) {
+            if (nvalid == 16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) yp[(size_t)(nb + j) * HWo] = val[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nvalid) yp[(size_t)(nb + j) * HWo] = val[j];
             }
           }
+          H_ACC(3);
         }
       }
       h_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      H_ACC(1);
+      if (CTR) cacc[5] += 1;
+    }
+    if (CTR && ctr && warp == 12 && lane == 0) {
+      ctr[24] = cacc[0]; ctr[25] = cacc[1]; ctr[26] = cacc[5]; ctr[27] = cacc[2]; ctr[28] = cacc[3];
     }
   }
 
@@ -593,11 +677,11 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-template <int KS, bool STAGED>
-static int launch_h16(const CUtensorMap& map, const HArgs& a, size_t smem, cudaStream_t st) {
+template <int KS, bool STAGED, bool CTR>
+static int launch_h16_(const CUtensorMap& map, const HArgs& a, size_t smem, cudaStream_t st) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_h16_kernel<KS, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_h16_kernel<KS, STAGED, CTR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
       return (int)e;
@@ -605,8 +689,12 @@ static int launch_h16(const CUtensorMap& map, const HArgs& a, size_t smem, cudaS
     attr_smem = smem;
   }
   int grid = a.items < sm_count() ? a.items : sm_count();
-  conv_h16_kernel<KS, STAGED><<<grid, H_THREADS, smem, st>>>(map, a);
+  conv_h16_kernel<KS, STAGED, CTR><<<grid, H_THREADS, smem, st>>>(map, a);
   return check_launch("irr_conv2d_fwd");
+}
+template <int KS, bool STAGED>
+static int launch_h16(const CUtensorMap& map, const HArgs& a, size_t smem, cudaStream_t st) {
+  return h_ctr_host ? launch_h16_<KS, STAGED, true>(map, a, smem, st) : launch_h16_<KS, STAGED, false>(map, a, smem, st);
 }
 
 // force_gather: testing hook (IRR_CONV_GATHER=1) so both producer variants can be exercised on any shape.
@@ -633,7 +721,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb;
   a.M = (long long)B * a.Ho * a.Wo;
   a.slope = slope; a.alpha = alpha;
-  const size_t misc = 54 * 8 + 256 * 4 + 64;
+  const size_t misc = 56 * 8 + 256 * 4 + 64;
   const size_t total_b = (size_t)g.nkb * g.img_bytes;
 
   CUtensorMap map;
@@ -699,3 +787,10 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
 }
 
 }  // namespace irr
+
+// Debug hook (not part of the ABI in include/irr_b200.h): point CTA 0's per-role cycle counters at `buf`
+// (32 x int64, device memory) or disable them with NULL.
+extern "C" int irrdbg_conv_counters(long long* buf) {
+  irr::h_ctr_host = buf;
+  return (int)cudaMemcpyToSymbol(irr::h_ctr_ptr, &buf, sizeof(buf));
+}

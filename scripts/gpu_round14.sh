@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "3xf16" 2>&1 | tail -15 > gpurun_out/h16_tests.log; cat gpurun_out/h16_tests.log
+timeout 300 python scripts/h16_counters.py > gpurun_out/h16_counters3.log 2>&1; cat gpurun_out/h16_counters3.log
+timeout 300 python scripts/bench_conv.py 3xf16 > gpurun_out/h16_bench_conv2.log 2>&1; cat gpurun_out/h16_bench_conv2.log
