@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — image-pairs/sec of the IRR-PWC inference hot path (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph] [--math fp32|3xtf32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph] [--math fp32|3xtf32|tf32|3xf16]
     N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
               bench.py --gpus N --steps K --warmup W
 
@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--math", default=os.environ.get("IRR_MATH", "auto"), choices=["auto", "fp32", "3xtf32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("IRR_MATH", "auto"), choices=["auto", "fp32", "3xtf32", "tf32", "3xf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     args = ap.parse_args()
@@ -201,11 +201,13 @@ def main():
     from irr_b200 import ops, pwc_modules
     from oracle import irr_oracle as O  # parameters / synthetic inputs only (shared with the reference arm)
 
-    math = {"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32, "tf32": ops.MATH_TC_TF32}.get(args.math)
-    if math is None:  # auto: fp32-grade tensor-core path when the library has it, CUDA cores otherwise
-        math = ops.MATH_TC_3XTF32 if ops.tc_supported(128, 128, 3, 1, 1) else ops.MATH_FP32_SIMT
+    math = {"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32, "tf32": ops.MATH_TC_TF32,
+            "3xf16": ops.MATH_TC_3XF16}.get(args.math)
+    if math is None:  # auto: the fp32-grade tensor-core path (3-term f16 split, TMA-staged activations)
+        math = ops.MATH_TC_3XF16
     pwc_modules.set_conv_math(math)
-    math_name = {0: "fp32 CUDA-core FFMA", 1: "tcgen05 3xTF32 (fp32-grade)", 2: "tcgen05 TF32"}[math]
+    math_name = {0: "fp32 CUDA-core FFMA", 1: "tcgen05 3xTF32 (fp32-grade)", 2: "tcgen05 TF32",
+                 3: "tcgen05 3xF16 split (fp32-grade), TMA-staged activations"}[math]
 
     B = args.batch
     model = irr_b200.IRR_PWC(None)
@@ -348,7 +350,7 @@ def main():
     if math == ops.MATH_FP32_SIMT:
         cpeak, cnote = 2 * 128 * 148 * 1.965e9 / 1e12, "nominal fp32 FFMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"
     else:
-        div = 6.0 if math == ops.MATH_TC_3XTF32 else 2.0
+        div = {ops.MATH_TC_3XTF32: 6.0, ops.MATH_TC_TF32: 2.0, ops.MATH_TC_3XF16: 3.0}[math]
         cpeak, cnote = pk["bf16_tflops_sustained"] / div, f"measured bf16 GEMM (sustained) / {div:g}"
     roof_conv = {"bound": "tensor" if math != ops.MATH_FP32_SIMT else "fp32-simt", "achieved": conv_fl / (conv_ms * 1e-3) / 1e12,
                  "peak": cpeak, "unit": "TFLOP/s", "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / cpeak, "peak_note": cnote,

@@ -44,7 +44,7 @@ class ConvBlock(nn.Sequential):
 
     def _math(self):
         m = _default_math
-        if m != ops.MATH_FP32_SIMT and not ops.tc_supported(self.cout, self.cin, self.ks, self.stride, self.dil):
+        if m != ops.MATH_FP32_SIMT and not ops.tc_supported(self.cout, self.cin, self.ks, self.stride, self.dil, m):
             m = ops.MATH_FP32_SIMT
         return m
 

@@ -24,11 +24,13 @@ def cat2(rec, key, l, cuda):
     return torch.cat([rec[f"l{l}.{key}_f"], rec[f"l{l}.{key}_b"]], 0).to(cuda).contiguous()
 
 
-@pytest.fixture(scope="module", params=["fp32", "3xtf32"], autouse=True)
+@pytest.fixture(scope="module", params=["fp32", "3xtf32", "3xf16"], autouse=True)
 def conv_math(request):
-    """Every model-level test runs twice: CUDA-core fp32 convs and the tcgen05 3xTF32 convs (fp32-grade)."""
+    """Every model-level test runs three times: CUDA-core fp32 convs, the tcgen05 3xTF32 convs and the tcgen05 3xF16
+    convs with TMA-staged activations (both fp32-grade; 3xF16 is the bench default)."""
     from irr_b200 import ops, pwc_modules
-    pwc_modules.set_conv_math(ops.MATH_FP32_SIMT if request.param == "fp32" else ops.MATH_TC_3XTF32)
+    pwc_modules.set_conv_math({"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32,
+                               "3xf16": ops.MATH_TC_3XF16}[request.param])
     yield request.param
     pwc_modules.set_conv_math(ops.MATH_FP32_SIMT)
 
