@@ -597,6 +597,331 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ rolling kernel
+// Thin single-chunk layers (Cin <= 32, Cout <= 64, 3x3, stride 1, dilation 1): the occlusion up-sampler's 32->32
+// chain at full resolution, 11->32, 32->1, 16->16 ...  These are HBM-bound by the algorithm (K = 288), but the item
+// kernel above re-reads every staged element nine times (once per tap) and issues 12 small MMAs per K block behind
+// two waits: shared-memory bandwidth and MMA issue, not HBM, set its pace (~1.9 TB/s).  Here a CTA walks DOWN a
+// 128-pixel-wide column strip instead:
+//   * one input row (32 ch x 136 px) is staged by TMA, split to f16 hi/lo in place, and copied to TMEM three times
+//     (kx = 0,1,2) — not nine: the row is the ky = 0 tap of output row r+1, the ky = 1 tap of row r and the ky = 2 tap
+//     of row r-1, so each A stage feeds three MMA groups that differ only in weights and accumulator;
+//   * four output-row accumulators rotate through TMEM ([0,256): 4 x 64 columns); three MMA-issuing warps, one per ky,
+//     work on three different accumulators at once.  Accumulators are zeroed by the epilogue when it drains them
+//     (every MMA accumulates), so there is no first-MMA ordering between the issuers;
+//   * the layer's nine weight images stay resident in shared memory; rows above/below the image arrive as TMA zeros,
+//     so every segment runs the same L+2 row schedule.
+// Roles: warps 0-3 producers (pixel = thread), 4-6 MMA issuers (ky), 7 loader, 8-11 epilogue.
+constexpr int R_THREADS = 384;
+constexpr int R_XS = 6;          // staged input rows in flight
+constexpr int R_SA = 8;          // A ring stages in TMEM (32 columns each) at column 256
+constexpr int R_PW = 136;        // staged row width: 4 (aligned left halo) + 128 + 1 (+3 pad)
+constexpr int R_XBYTES = H_CK * R_PW * 4;
+
+struct RArgs {
+  const float* x; long long x_bs;
+  const uint8_t* wp;
+  const float* bias;
+  const float* addend; long long a_bs;
+  float* y; long long y_bs;
+  int B, Cin, H, W, Cout, n_tile;
+  int L, segs, xtiles, items;
+  float slope, alpha;
+};
+
+template <int NG, bool CTR>
+__global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_constant__ CUtensorMap xmap, RArgs p) {
+  extern __shared__ __align__(1024) uint8_t r_smem[];
+  const int N = p.n_tile;
+  const uint32_t img_bytes = (uint32_t)N * 128;
+  uint8_t* smem_w = r_smem;                                  // 9 weight images, 1024-aligned
+  uint8_t* smem_x = r_smem + 9 * img_bytes;                  // R_XS staged rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_x + R_XS * R_XBYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto x_full = [&](int s) { return bar0 + 8u * s; };                 // [0, 6)
+  auto x_empty = [&](int s) { return bar0 + 8u * (6 + s); };          // [6, 12)
+  auto a_full = [&](int s) { return bar0 + 8u * (12 + s); };          // [12, 20)
+  auto a_empty = [&](int s) { return bar0 + 8u * (20 + s); };         // [20, 28)
+  auto acc_full = [&](int s) { return bar0 + 8u * (28 + s); };        // [28, 32)
+  auto acc_empty = [&](int s) { return bar0 + 8u * (32 + s); };       // [32, 36)
+  const uint32_t w_full = bar0 + 8u * 36;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 38);
+  float* bias_s = reinterpret_cast<float*>(bars + 40);       // 64 floats, 16-byte aligned
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* ctr = (CTR && blockIdx.x == 0) ? h_ctr_ptr : nullptr;
+  long long cacc[6] = {0, 0, 0, 0, 0, 0};
+  (void)ctr; (void)cacc;
+  if (tid < 64) bias_s[tid] = tid < p.Cout ? __ldg(p.bias + tid) : 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < R_XS; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 4); }
+    for (int s = 0; s < R_SA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 3); }
+    for (int s = 0; s < 4; ++s) { mbar_init(acc_full(s), 3); mbar_init(acc_empty(s), 4); }
+    mbar_init(w_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(H_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  h_fence_before();
+  __syncthreads();
+  h_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const float inv_scale = __ldg(reinterpret_cast<const float*>(p.wp) + 1);
+  const int HW = p.H * p.W;
+  const int per_img = p.segs * p.xtiles;
+
+  auto item_decode = [&](int item, int& b, int& ya, int& nr, int& x0) {
+    b = item / per_img;
+    const int r = item - b * per_img;
+    const int seg = r / p.xtiles;
+    x0 = (r - seg * p.xtiles) * 128;
+    ya = seg * p.L;
+    nr = min(p.L, p.H - ya);
+  };
+
+  if (warp < 4) {
+    // ======================= producers: split the staged row in place, copy three shifted views to TMEM ==========
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int cx = 0, ca = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, ya, nr, x0;
+      item_decode(item, b, ya, nr, x0);
+      for (int i = 0; i < nr + 2; ++i, ++cx) {
+        const int sx = cx % R_XS;
+        H_T0();
+        mbar_wait(x_full(sx), (uint32_t)((cx / R_XS) & 1));
+        H_ACC(0);
+        float* xs = reinterpret_cast<float*>(smem_x + (size_t)sx * R_XBYTES);
+        // in-place split: plane 2k <- {hi(2k), hi(2k+1)}, plane 2k+1 <- {lo(2k), lo(2k+1)}; units = (position, 4 pairs)
+        for (int u = tid; u < 4 * R_PW; u += 128) {
+          const int pg = u / R_PW, pos = u - pg * R_PW;
+          float* base = xs + (pg * 8) * R_PW + pos;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = base[j * R_PW];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t hi = h_pack(v[2 * k], v[2 * k + 1]);
+            float f0, f1;
+            h_unpack(hi, f0, f1);
+            const uint32_t lo = h_pack(v[2 * k] - f0, v[2 * k + 1] - f1);
+            base[(2 * k) * R_PW] = __uint_as_float(hi);
+            base[(2 * k + 1) * R_PW] = __uint_as_float(lo);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        H_ACC(1);
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + tid + 3;  // column of tap kx = 0 (4 - pad)
+#pragma unroll 1
+        for (int kx = 0; kx < 3; ++kx, ++ca) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            hi[k] = xw[(2 * k) * R_PW + kx];
+            lo[k] = xw[(2 * k + 1) * R_PW + kx];
+          }
+          const int sa = ca % R_SA;
+          H_ACC(2);
+          mbar_wait(a_empty(sa), (uint32_t)(((ca / R_SA) & 1) ^ 1));
+          h_fence_after();
+          H_ACC(3);
+          const uint32_t a_addr = lane_addr + (uint32_t)(H_A_COL + sa * 32);
+          h_tmem_st16(a_addr, hi);
+          h_tmem_st16(a_addr + 16, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          h_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(sa));
+          H_ACC(4);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_empty(sx));
+        if (CTR) cacc[5] += 1;
+      }
+    }
+    if (CTR && ctr && warp == 0 && lane == 0)
+      for (int i = 0; i < 6; ++i) ctr[i] = cacc[i];
+  } else if (warp < 7) {
+    // ======================= MMA issuers: warp 4+ky adds tap row ky of every staged row to output row r+1-ky ======
+    const int ky = warp - 4;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const bool two = p.Cin > 16;
+    mbar_wait(w_full, 0);
+    int ca = 0, obase = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, ya, nr, x0;
+      item_decode(item, b, ya, nr, x0);
+      for (int i = 0; i < nr + 2; ++i) {
+        const int oi = i - ky;                 // output row (inside the segment) this input row feeds through tap ky
+        const bool valid = oi >= 0 && oi < nr;
+        const int og = obase + oi;             // running output-row counter -> accumulator slot and phase
+        const int slot = og & 3;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 64);
+#pragma unroll 1
+        for (int kx = 0; kx < 3; ++kx, ++ca) {
+          const int sa = ca % R_SA;
+          H_T0();
+          mbar_wait(a_full(sa), (uint32_t)((ca / R_SA) & 1));
+          H_ACC(0);
+          if (valid && kx == 0) mbar_wait(acc_empty(slot), (uint32_t)((og >> 2) & 1));  // drained and zeroed
+          h_fence_after();
+          H_ACC(1);
+          if (h_elect()) {
+            if (valid) {
+              const uint64_t bd = h_b_desc(smem_u32(smem_w) + (uint32_t)(ky * 3 + kx) * img_bytes);
+              const uint32_t a_hi = tmem_base + (uint32_t)(H_A_COL + sa * 32);
+              h_mma_ts(d_tmem, a_hi + 16, bd, idesc, 1u);   // lo * hi
+              h_mma_ts(d_tmem, a_hi, bd + 4, idesc, 1u);    // hi * lo
+              h_mma_ts(d_tmem, a_hi, bd, idesc, 1u);        // hi * hi
+              if (two) {
+                h_mma_ts(d_tmem, a_hi + 24, bd + 2, idesc, 1u);
+                h_mma_ts(d_tmem, a_hi + 8, bd + 6, idesc, 1u);
+                h_mma_ts(d_tmem, a_hi + 8, bd + 2, idesc, 1u);
+              }
+              h_commit(a_empty(sa));
+              if (kx == 2) h_commit(acc_full(slot));
+            } else {
+              mbar_arrive(a_empty(sa));
+            }
+          }
+          __syncwarp();
+          H_ACC(2);
+          if (CTR) cacc[5] += 1;
+        }
+      }
+      obase += nr;
+    }
+    if (CTR && ctr && lane == 0)
+      for (int i = 0; i < 6; ++i) ctr[8 + 6 * ky + i] = cacc[i];
+  } else if (warp == 7) {
+    // ======================= loader: weights once, then one TMA row per schedule step =======================
+    if (h_elect()) {
+      mbar_expect_tx(w_full, 9 * img_bytes);
+      for (int t = 0; t < 9; ++t)
+        h_bulk_g2s(smem_u32(smem_w) + (uint32_t)t * img_bytes, p.wp + H_HDR + (size_t)t * img_bytes, img_bytes, w_full);
+    }
+    __syncwarp();
+    int cx = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, ya, nr, x0;
+      item_decode(item, b, ya, nr, x0);
+      for (int i = 0; i < nr + 2; ++i, ++cx) {
+        const int sx = cx % R_XS;
+        mbar_wait(x_empty(sx), (uint32_t)(((cx / R_XS) & 1) ^ 1));
+        if (h_elect()) {
+          mbar_expect_tx(x_full(sx), R_XBYTES);
+          h_tma_4d(smem_u32(smem_x) + (uint32_t)sx * R_XBYTES, &xmap, x0 - 4, ya - 1 + i, 0, b, x_full(sx));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================= epilogue: drain + re-zero the accumulator, then bias / act / residual / store ========
+    const int q = warp & 3;
+    const int t = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float slope = p.slope, alpha = p.alpha;
+    const bool has_add = p.addend != nullptr;
+    const int cfull = p.Cout >> 4, ctail = p.Cout & 15;   // full 16-channel groups, channels in the partial group
+    uint32_t zero[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) zero[j] = 0u;
+    for (int c0 = 0; c0 < 256; c0 += 16) h_tmem_st16(lane_addr + (uint32_t)c0, zero);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    h_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int s = 0; s < 4; ++s) mbar_arrive(acc_empty(s));
+    int og = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, ya, nr, x0;
+      item_decode(item, b, ya, nr, x0);
+      const int ox = x0 + t;
+      const bool m_ok = ox < p.W;
+      for (int oi = 0; oi < nr; ++oi, ++og) {
+        const int slot = og & 3;
+        const size_t opix = (size_t)(ya + oi) * p.W + (m_ok ? ox : 0);
+        float* yp = p.y + (size_t)b * p.y_bs + opix;
+        // residual operand first: its loads are in flight while the row's last MMAs finish
+        float add[NG * 16];
+#pragma unroll
+        for (int j = 0; j < NG * 16; ++j) add[j] = 0.f;
+        if (has_add) {
+          const float* ap = p.addend + (size_t)b * p.a_bs + opix;
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (g < cfull) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) add[g * 16 + j] = __ldg(ap + (size_t)(g * 16 + j) * HW);
+            } else if (g == cfull) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ctail) add[g * 16 + j] = __ldg(ap + (size_t)(g * 16 + j) * HW);
+            }
+          }
+        }
+        H_T0();
+        mbar_wait(acc_full(slot), (uint32_t)((og >> 2) & 1));
+        h_fence_after();
+        H_ACC(0);
+        const uint32_t acc_addr = lane_addr + (uint32_t)(slot * 64);
+        uint32_t r[NG * 16];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) h_tmem_ld16(acc_addr + (uint32_t)(g * 16), r + g * 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < NG; ++g) h_tmem_st16(acc_addr + (uint32_t)(g * 16), zero);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        h_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(slot));
+        H_ACC(1);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float bs[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + g * 16 + 4 * j);
+            bs[4 * j] = b4.x; bs[4 * j + 1] = b4.y; bs[4 * j + 2] = b4.z; bs[4 * j + 3] = b4.w;
+          }
+          float val[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaf(__uint_as_float(r[g * 16 + j]), inv_scale, bs[j]);
+            val[j] = fmaf(leaky(a, slope), alpha, add[g * 16 + j]);
+          }
+          if (m_ok) {
+            if (g < cfull) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) yp[(size_t)(g * 16 + j) * HW] = val[j];
+            } else if (g == cfull) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ctail) yp[(size_t)(g * 16 + j) * HW] = val[j];
+            }
+          }
+        }
+        H_ACC(2);
+        if (CTR) cacc[5] += 1;
+      }
+    }
+    if (CTR && ctr && warp == 8 && lane == 0)
+      for (int i = 0; i < 6; ++i) ctr[26 + i] = cacc[i];
+  }
+
+  h_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    h_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H_TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight packer
 // Pass 1: max|w| of the layer -> header {max_abs, inv_scale, scale}, scale = 2^(14 - floor(log2(max))).
 __global__ void h16_scale_kernel(const float* __restrict__ w, float* __restrict__ hdr, long long n) {
@@ -697,7 +1022,30 @@ static int launch_h16(const CUtensorMap& map, const HArgs& a, size_t smem, cudaS
   return h_ctr_host ? launch_h16_<KS, STAGED, true>(map, a, smem, st) : launch_h16_<KS, STAGED, false>(map, a, smem, st);
 }
 
+template <int NG, bool CTR>
+static int launch_roll(const CUtensorMap& map, const RArgs& r, size_t smem, int grid, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_roll_kernel<NG, CTR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_smem = smem;
+  }
+  conv_roll_kernel<NG, CTR><<<grid, R_THREADS, smem, st>>>(map, r);
+  return check_launch("irr_conv2d_fwd");
+}
+
 // force_gather: testing hook (IRR_CONV_GATHER=1) so both producer variants can be exercised on any shape.
+static bool no_roll() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRR_CONV_NO_ROLL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 static bool force_gather() {
   static int v = -1;
   if (v < 0) {
@@ -727,6 +1075,42 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   EncodeTiledFn enc = encode_tiled();
+  const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
+                      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
+  // ---- rolling kernel: single-chunk thin layers on wide images
+  if (tma_ok && !no_roll() && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 64 && W >= 96) {
+    RArgs r;
+    memset(&r, 0, sizeof(r));
+    r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
+    r.B = B; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.n_tile = g.n_tile;
+    r.slope = slope; r.alpha = alpha;
+    r.xtiles = (W + 127) / 128;
+    int L = 32;
+    while (L > 4 && (long long)B * r.xtiles * ((H + L - 1) / L) < 3LL * sm_count()) L >>= 1;
+    r.L = L;
+    r.segs = (H + L - 1) / L;
+    r.items = B * r.xtiles * r.segs;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)x_bs * 4};
+    cuuint32_t box[4] = {(cuuint32_t)R_PW, 1, (cuuint32_t)H_CK, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS) {
+      const size_t rsmem = 9 * g.img_bytes + (size_t)R_XS * R_XBYTES + 40 * 8 + 64 * 4 + 64;
+      const int grid = r.items < sm_count() ? r.items : sm_count();
+      const bool dbg = h_ctr_host != nullptr;
+      int rc;
+      switch (g.n_tile / 16) {
+        case 1: rc = dbg ? launch_roll<1, true>(map, r, rsmem, grid, st) : launch_roll<1, false>(map, r, rsmem, grid, st); break;
+        case 2: rc = dbg ? launch_roll<2, true>(map, r, rsmem, grid, st) : launch_roll<2, false>(map, r, rsmem, grid, st); break;
+        case 3: rc = dbg ? launch_roll<3, true>(map, r, rsmem, grid, st) : launch_roll<3, false>(map, r, rsmem, grid, st); break;
+        default: rc = dbg ? launch_roll<4, true>(map, r, rsmem, grid, st) : launch_roll<4, false>(map, r, rsmem, grid, st); break;
+      }
+      return rc;
+    }
+  }
   bool staged = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   if (staged) {

@@ -270,6 +270,9 @@ H16_CASES = TC_CASES + [
     (1, 64, 109, 256, 64, 3, 1, 1), (2, 128, 30, 256, 128, 3, 1, 2), (1, 40, 20, 512, 32, 3, 1, 1),
     (1, 32, 12, 16, 16, 3, 1, 1), (1, 48, 9, 8, 32, 3, 1, 1), (2, 128, 28, 64, 128, 3, 1, 4), (1, 96, 33, 132, 96, 3, 1, 2),
     (1, 33, 7, 260, 48, 1, 1, 1), (6, 243, 55, 128, 128, 3, 1, 1), (3, 64, 50, 1024, 32, 3, 1, 1),
+    # row-rolling kernel (Cin <= 32, Cout <= 64, W >= 96): partial strips, short/long segments, one- and two-step K
+    (2, 32, 37, 256, 32, 3, 1, 1), (1, 11, 50, 512, 32, 3, 1, 1), (2, 32, 20, 132, 1, 3, 1, 1), (1, 16, 33, 128, 16, 3, 1, 1),
+    (1, 32, 70, 1024, 64, 3, 1, 1), (16, 32, 109, 256, 9, 3, 1, 1), (5, 3, 45, 100, 40, 3, 1, 1),
 ]
 
 
@@ -292,6 +295,23 @@ def test_conv2d_3xf16_vs_torch_cpu(cuda, case):
     refmax = ref.abs().max().item()
     print(f"[h16] {case}: max-abs {err:.3e} (|ref|max {refmax:.2f})")
     assert err <= 5e-5 * max(2.0, refmax)
+
+
+def test_conv2d_3xf16_rolling_slices_addend(cuda):
+    """Row-rolling kernel writing into / reading from channel slices with the residual epilogue (occlusion up-sampler)."""
+    from irr_b200 import ops
+    B, Ct, H, W = 3, 50, 45, 200
+    buf = torch.from_numpy(rs(61, (B, Ct, H, W))).to(cuda)
+    w = torch.from_numpy(rs(62, (32, 32, 3, 3))) * 0.06
+    b = torch.from_numpy(rs(63, (32,))) * 0.1
+    add = torch.from_numpy(rs(64, (B, 40, H, W))).to(cuda)
+    ref = add[:, 4:36].cpu() + 0.1 * torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(buf[:, 10:42].cpu(), w, b, padding=1), 0.1)
+    out = torch.zeros((B, 44, H, W), device=cuda)
+    ops.conv2d(buf[:, 10:42], ops.pack_weights(w.to(cuda), ops.MATH_TC_3XF16), b.to(cuda), 32, 3, slope=0.1,
+               out=out[:, 7:39], addend=add[:, 4:36], alpha=0.1, math=ops.MATH_TC_3XF16)
+    assert (out[:, 7:39].cpu() - ref).abs().max().item() <= 1e-4
+    assert (out[:, :7] == 0).all() and (out[:, 39:] == 0).all()
 
 
 def test_conv2d_3xf16_slices_addend(cuda):
