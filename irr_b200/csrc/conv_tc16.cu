@@ -289,23 +289,37 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           H_ACC(0);
           float* xs = reinterpret_cast<float*>(smem_x + (size_t)(g % H_SX) * p.x_stage_bytes);
           // units of (position, group of 4 channel pairs), consecutive threads on consecutive positions
+          // Two units per trip, all loads before the math before the stores: the compiler cannot prove the in-place
+          // stores do not alias the next unit's loads and would otherwise serialise the load -> split -> store chains.
           int pos = tid, pg = 0;
           while (pos >= chp) { pos -= chp; ++pg; }
           while (pg < 4) {
-            float* base = xs + (size_t)(pg * 8) * chp + pos;
-            float v[8];
+            float* base0 = xs + (size_t)(pg * 8) * chp + pos;
+            int pos1 = pos + 256, pg1 = pg;
+            while (pos1 >= chp) { pos1 -= chp; ++pg1; }
+            const bool second = pg1 < 4;
+            float* base1 = second ? xs + (size_t)(pg1 * 8) * chp + pos1 : base0;
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = base[j * chp];
+            for (int j = 0; j < 8; ++j) v[j] = base0[j * chp];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int j = 0; j < 8; ++j) v[8 + j] = base1[j * chp];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
               const uint32_t hi = h_pack(v[2 * k], v[2 * k + 1]);
               float f0, f1;
               h_unpack(hi, f0, f1);
               const uint32_t lo = h_pack(v[2 * k] - f0, v[2 * k + 1] - f1);  // exact residuals, rounded to f16
-              base[(2 * k) * chp] = __uint_as_float(hi);
-              base[(2 * k + 1) * chp] = __uint_as_float(lo);
+              v[2 * k] = __uint_as_float(hi);
+              v[2 * k + 1] = __uint_as_float(lo);
             }
-            pos += 256;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) base0[j * chp] = v[j];
+            if (second) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) base1[j * chp] = v[8 + j];
+            }
+            pos = pos1 + 256; pg = pg1;
             while (pos >= chp) { pos -= chp; ++pg; }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps: tile fully converted
@@ -611,8 +625,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
 //     (every MMA accumulates), so there is no first-MMA ordering between the issuers;
 //   * the layer's nine weight images stay resident in shared memory; rows above/below the image arrive as TMA zeros,
 //     so every segment runs the same L+2 row schedule.
-// Roles: warps 0-3 producers (pixel = thread), 4-6 MMA issuers (ky), 7 loader, 8-11 epilogue.
-constexpr int R_THREADS = 384;
+// Roles: warps 0-7 producers (two groups of four on alternate rows, pixel = thread), 8-10 MMA issuers (ky), 11 loader,
+// 12-15 epilogue.
+constexpr int R_THREADS = 512;
 constexpr int R_XS = 6;          // staged input rows in flight
 constexpr int R_SA = 8;          // A ring stages in TMEM (32 columns each) at column 256
 constexpr int R_PW = 136;        // staged row width: 4 (aligned left halo) + 128 + 1 (+3 pad)
@@ -654,13 +669,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
   (void)ctr; (void)cacc;
   if (tid < 64) bias_s[tid] = tid < p.Cout ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < R_XS; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 4); }
+    for (int s = 0; s < R_XS; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 4); }  // 4 warps of the owning group
     for (int s = 0; s < R_SA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 3); }
     for (int s = 0; s < 4; ++s) { mbar_init(acc_full(s), 3); mbar_init(acc_empty(s), 4); }
     mbar_init(w_full, 1);
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(H_TMEM_COLS)
                  : "memory");
@@ -683,41 +698,58 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     nr = min(p.L, p.H - ya);
   };
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ======================= producers: split the staged row in place, copy three shifted views to TMEM ==========
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int cx = 0, ca = 0;
+    // Two groups of four warps take alternate rows (row counter parity); stage indices stay the global sequence.
+    const int grp = warp >> 2, q = warp & 3;
+    const int pt = q * 32 + lane;                // pixel of this thread inside the strip
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    int cx = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, ya, nr, x0;
       item_decode(item, b, ya, nr, x0);
       for (int i = 0; i < nr + 2; ++i, ++cx) {
+        if ((cx & 1) != grp) continue;
         const int sx = cx % R_XS;
         H_T0();
         mbar_wait(x_full(sx), (uint32_t)((cx / R_XS) & 1));
         H_ACC(0);
         float* xs = reinterpret_cast<float*>(smem_x + (size_t)sx * R_XBYTES);
-        // in-place split: plane 2k <- {hi(2k), hi(2k+1)}, plane 2k+1 <- {lo(2k), lo(2k+1)}; units = (position, 4 pairs)
-        for (int u = tid; u < 4 * R_PW; u += 128) {
-          const int pg = u / R_PW, pos = u - pg * R_PW;
-          float* base = xs + (pg * 8) * R_PW + pos;
-          float v[8];
+        // in-place split: plane 2k <- {hi(2k), hi(2k+1)}, plane 2k+1 <- {lo(2k), lo(2k+1)}.
+        // 16 pairs x 136 positions = 17 (pair, position) units per thread, consecutive threads on consecutive positions
+        // (all loads first, then the math, then all stores: the compiler cannot prove the in-place stores do not
+        // alias later loads and would otherwise serialise the 17 load -> split -> store chains)
+        float cv0[17], cv1[17];
+        int coff[17];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = base[j * R_PW];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t hi = h_pack(v[2 * k], v[2 * k + 1]);
-            float f0, f1;
-            h_unpack(hi, f0, f1);
-            const uint32_t lo = h_pack(v[2 * k] - f0, v[2 * k + 1] - f1);
-            base[(2 * k) * R_PW] = __uint_as_float(hi);
-            base[(2 * k + 1) * R_PW] = __uint_as_float(lo);
-          }
+        for (int it = 0; it < 17; ++it) {
+          const int u = pt + 128 * it;
+          const int pr = u / R_PW, pos = u - pr * R_PW;
+          coff[it] = (2 * pr) * R_PW + pos;
+          cv0[it] = xs[coff[it]];
+          cv1[it] = xs[coff[it] + R_PW];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int it = 0; it < 17; ++it) {
+          const uint32_t hi = h_pack(cv0[it], cv1[it]);
+          float f0, f1;
+          h_unpack(hi, f0, f1);
+          const uint32_t lo = h_pack(cv0[it] - f0, cv1[it] - f1);
+          cv0[it] = __uint_as_float(hi);
+          cv1[it] = __uint_as_float(lo);
+        }
+#pragma unroll
+        for (int it = 0; it < 17; ++it) {
+          xs[coff[it]] = cv0[it];
+          xs[coff[it] + R_PW] = cv1[it];
+        }
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         H_ACC(1);
-        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + tid + 3;  // column of tap kx = 0 (4 - pad)
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + pt + 3;  // column of tap kx = 0 (4 - pad)
 #pragma unroll 1
-        for (int kx = 0; kx < 3; ++kx, ++ca) {
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ca = 3 * cx + kx;
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -746,9 +778,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     }
     if (CTR && ctr && warp == 0 && lane == 0)
       for (int i = 0; i < 6; ++i) ctr[i] = cacc[i];
-  } else if (warp < 7) {
-    // ======================= MMA issuers: warp 4+ky adds tap row ky of every staged row to output row r+1-ky ======
-    const int ky = warp - 4;
+  } else if (warp < 11) {
+    // ======================= MMA issuers: warp 8+ky adds tap row ky of every staged row to output row r+1-ky ======
+    const int ky = warp - 8;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const bool two = p.Cin > 16;
     mbar_wait(w_full, 0);
@@ -798,7 +830,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     }
     if (CTR && ctr && lane == 0)
       for (int i = 0; i < 6; ++i) ctr[8 + 6 * ky + i] = cacc[i];
-  } else if (warp == 7) {
+  } else if (warp == 11) {
     // ======================= loader: weights once, then one TMA row per schedule step =======================
     if (h_elect()) {
       mbar_expect_tx(w_full, 9 * img_bytes);
@@ -910,13 +942,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         if (CTR) cacc[5] += 1;
       }
     }
-    if (CTR && ctr && warp == 8 && lane == 0)
+    if (CTR && ctr && warp == 12 && lane == 0)
       for (int i = 0; i < 6; ++i) ctr[26 + i] = cacc[i];
   }
 
   h_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     h_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H_TMEM_COLS) : "memory");
   }
@@ -1078,7 +1110,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   // ---- rolling kernel: single-chunk thin layers on wide images
-  if (tma_ok && !no_roll() && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 64 && W >= 96) {
+  if (tma_ok && !no_roll() && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
     RArgs r;
     memset(&r, 0, sizeof(r));
     r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
@@ -1102,12 +1134,8 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
       const int grid = r.items < sm_count() ? r.items : sm_count();
       const bool dbg = h_ctr_host != nullptr;
       int rc;
-      switch (g.n_tile / 16) {
-        case 1: rc = dbg ? launch_roll<1, true>(map, r, rsmem, grid, st) : launch_roll<1, false>(map, r, rsmem, grid, st); break;
-        case 2: rc = dbg ? launch_roll<2, true>(map, r, rsmem, grid, st) : launch_roll<2, false>(map, r, rsmem, grid, st); break;
-        case 3: rc = dbg ? launch_roll<3, true>(map, r, rsmem, grid, st) : launch_roll<3, false>(map, r, rsmem, grid, st); break;
-        default: rc = dbg ? launch_roll<4, true>(map, r, rsmem, grid, st) : launch_roll<4, false>(map, r, rsmem, grid, st); break;
-      }
+      if (g.n_tile == 16) rc = dbg ? launch_roll<1, true>(map, r, rsmem, grid, st) : launch_roll<1, false>(map, r, rsmem, grid, st);
+      else rc = dbg ? launch_roll<2, true>(map, r, rsmem, grid, st) : launch_roll<2, false>(map, r, rsmem, grid, st);
       return rc;
     }
   }
