@@ -109,6 +109,18 @@ int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const f
                    long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
                    int stride, int dilation, float leaky_slope, float alpha, int math, irr_stream_t stream);
 
+/* Same, with an optional scratch buffer that lets the tensor-core path split the K loop of a layer over several CTAs
+ * when the layer has far fewer output tiles than the GPU has SMs (the 7x16 ... 14x32 pyramid levels): partial sums go
+ * to `workspace`, a second launch adds them in a fixed order and applies the epilogue (deterministic).  workspace may
+ * be NULL (never split).  irr_conv2d_workspace_bytes returns the size that allows every split this shape may use
+ * (0 = never split); the buffer is caller-owned device memory, 16-byte aligned, private to the call until it
+ * completes on `stream`. */
+size_t irr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ksize, int stride, int dilation, int math);
+int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
+                      long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
+                      int stride, int dilation, float leaky_slope, float alpha, int math, void* workspace,
+                      size_t workspace_bytes, irr_stream_t stream);
+
 /* A8 — upsample2d_as (models/pwc_modules.py:65-67): bilinear, align_corners=True, any in/out size, fused with an
  * optional per-channel-parity scale (even channels * scale_even, odd * scale_odd): rescale_flow of
  * pwc_modules.py:70-82 applied to the resized flow, or the final *(1/div_flow) of IRR_PWC.py:176. */

@@ -35,6 +35,9 @@ PROTOTYPES = {
     "irr_conv2d_pack_weights": [c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp],
     "irr_conv2d_fwd": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                        c_f, c_i, c_fp],
+    "irr_conv2d_workspace_bytes": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i],
+    "irr_conv2d_fwd_ws": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
+                          c_f, c_i, c_fp, C.c_size_t, c_fp],
     "irr_resize_bilinear_ac_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_fp],
     "irr_scale_channels_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_f, c_f, c_fp],
     "irr_upsample_nearest2x_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
@@ -42,7 +45,8 @@ PROTOTYPES = {
     "irr_channel_l2norm_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],
     "irr_refine_gather_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
 }
-_RESTYPES = {"irr_last_error": C.c_char_p, "irr_conv2d_packed_bytes": C.c_size_t}
+_RESTYPES = {"irr_last_error": C.c_char_p, "irr_conv2d_packed_bytes": C.c_size_t,
+             "irr_conv2d_workspace_bytes": C.c_size_t}
 
 _lib = None
 

@@ -18,7 +18,8 @@ size_t h16_packed_bytes(int Cout, int Cin, int ks);
 int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st);
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
              float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
-             float alpha, cudaStream_t st);
+             float alpha, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil);
 }  // namespace irr
 
 using namespace irr;
@@ -58,9 +59,24 @@ int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int C
   return fail_arg(fn, "unknown math mode");
 }
 
+size_t irr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ksize, int stride, int dilation, int math) {
+  if (math != IRR_MATH_TC_3XF16 || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || Cout > 256 ||
+      (ksize != 1 && ksize != 3) || stride < 1 || dilation < 1)
+    return 0;
+  return h16_workspace_bytes(B, Cin, H, W, Cout, ksize, stride, dilation);
+}
+
 int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
                    long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
                    int stride, int dilation, float leaky_slope, float alpha, int math, irr_stream_t stream) {
+  return irr_conv2d_fwd_ws(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride,
+                           dilation, leaky_slope, alpha, math, nullptr, 0, stream);
+}
+
+int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
+                      long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
+                      int stride, int dilation, float leaky_slope, float alpha, int math, void* workspace,
+                      size_t workspace_bytes, irr_stream_t stream) {
   const char* fn = "irr_conv2d_fwd";
   IRR_REQUIRE(x && w_packed && bias && y, fn, "null pointer");
   IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
@@ -84,7 +100,7 @@ int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const f
       return IRR_E_UNSUPPORTED;
     }
     return h16_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
-                    leaky_slope, alpha, as_stream(stream));
+                    leaky_slope, alpha, workspace, workspace_bytes, as_stream(stream));
   }
   return fail_arg(fn, "unknown math mode");
 }

@@ -60,6 +60,8 @@ struct HArgs {
   int n_tile, n_tiles, cchunks, nkb, sb, resident;
   unsigned b_smem_bytes, x_stage_bytes;
   int rw_log2, rh, R, PW, padl, split, ytiles, xtiles, m_items, items;
+  int ksplit, cps;            // split-K: K chunks are dealt to `ksplit` CTAs per tile, `cps` chunks each
+  float* ws; long long ws_stride;  // split-K partial sums [ksplit][B][Cout][Ho*Wo] (raw accumulators)
   long long M;
   float slope, alpha;
 };
@@ -181,7 +183,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
   const int m_items = p.m_items;
   const int items = p.items;
   const int TPS = STAGED ? (p.split ? KS : T) : 1;   // K blocks (taps) served by one activation stage
-  const int spi = STAGED ? nkb / TPS : 0;             // activation stages per work item
 
   uint8_t* smem_b = h_smem;                            // 1024-aligned weight images
   uint8_t* smem_x = h_smem + p.b_smem_bytes;           // activation tiles (128-aligned)
@@ -240,6 +241,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
 
   // Work-item decode.  STAGED: item -> (n tile, image b, tile row ty, tile column tx); a half is RH rows x RW columns.
   // GATHER: item -> (n tile, linear 256-pixel block).
+  // Split-K (coarse pyramid levels, where a layer has fewer tiles than the GPU has SMs): item -> (K split sp, rest);
+  // split sp accumulates chunks [sp*cps, min(cchunks, (sp+1)*cps)) and stores RAW accumulators to its workspace
+  // slice; h16_splitk_finish sums the slices in a fixed order and applies the epilogue.
+  const int items_per_split = p.n_tiles * m_items;
   auto item_origin = [&](int item, int& nt, int& b, int& y0, int& x0) {
     nt = item / m_items;
     int r = item - nt * m_items;
@@ -267,8 +272,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
     int c = 0;
     int gx = 0;          // activation stages seen so far (all producer warps walk every stage)
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      int tin = 0, tap = 0, cc = 0;
-      for (int kb = 0; kb < nkb; ++kb, ++c) {
+      const int sp = item / items_per_split, it = item - sp * items_per_split;
+      const int cc0 = sp * p.cps, kb0 = cc0 * T, kb1 = min(p.cchunks, cc0 + p.cps) * T;
+      int tin = 0, tap = 0, cc = cc0;
+      for (int kb = kb0; kb < kb1; ++kb, ++c) {
         const int ky = tap / KS, kx = tap - ky * KS;
         const int my_cc = cc, my_tin = tin;
         if (++tap == T) { tap = 0; ++cc; }
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
         } else {
           if (item != cur_item) {  // decode this thread's two output pixels (linear pixel blocks)
             cur_item = item;
-            const int mt = item % m_items;
+            const int mt = it % m_items;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const long long mg = (long long)mt * 256 + h * 128 + t;
@@ -425,8 +432,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
       mbar_wait(acc_empty(buf), (uint32_t)((use & 1) ^ 1));
       H_ACC(0);
       const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 2 + h) * acc_stride);
-      int tap = 0, cc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int sp = item / items_per_split;
+      const int cc0 = sp * p.cps, kb0 = cc0 * T, kb1 = min(p.cchunks, cc0 + p.cps) * T;
+      int tap = 0, cc = cc0;
+      for (int kb = kb0; kb < kb1; ++kb) {
         const bool two = cc < p.cchunks - 1 || nk_last == 2;
         uint32_t b_addr;
         H_RST();
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
         H_ACC(2);
         if (h_elect()) {
           // K step j: A hi columns [8j, 8j+8), A lo columns [16+8j, ..); B hi bytes [32j, ..), B lo bytes [64+32j, ..)
-          h_mma_ts(d_tmem, a_hi + 16, bd, idesc, kb ? 1u : 0u);  // lo * hi
+          h_mma_ts(d_tmem, a_hi + 16, bd, idesc, kb != kb0 ? 1u : 0u);  // lo * hi
           h_mma_ts(d_tmem, a_hi, bd + 4, idesc, 1u);             // hi * lo
           h_mma_ts(d_tmem, a_hi, bd, idesc, 1u);                 // hi * hi
           if (two) {
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           }
           h_commit(a_empty(s));
           if (!resident) h_commit(b_empty(sb));
-          if (kb == nkb - 1) h_commit(acc_full(buf));
+          if (kb == kb1 - 1) h_commit(acc_full(buf));
         }
         __syncwarp();
         if (++s == H_SA) { s = 0; a_par ^= 1; }
@@ -477,9 +486,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
         int sb = 0;
         uint32_t par = 1;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-          const int nt = item / m_items;
+          const int sp = item / items_per_split, it = item - sp * items_per_split;
+          const int cc0 = sp * p.cps, kb0 = cc0 * T, kb1 = min(p.cchunks, cc0 + p.cps) * T;
+          const int nt = it / m_items;
           const uint8_t* src = wimg + (size_t)nt * nkb * img_bytes;
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(b_empty(sb), par);
             mbar_expect_tx(b_full(sb), img_bytes);
             h_bulk_g2s(smem_u32(smem_b) + (uint32_t)sb * img_bytes, src + (size_t)kb * img_bytes, img_bytes, b_full(sb));
@@ -495,8 +506,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
       int g = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int nt, b, y0, x0;
-        item_origin(item, nt, b, y0, x0);
-        for (int sidx = 0; sidx < spi; ++sidx, ++g) {
+        const int sp = item / items_per_split, it = item - sp * items_per_split;
+        const int cc0 = sp * p.cps, kb0 = cc0 * T, kb1 = min(p.cchunks, cc0 + p.cps) * T;
+        item_origin(it, nt, b, y0, x0);
+        for (int sidx = kb0 / TPS; sidx < kb1 / TPS; ++sidx, ++g) {
           const int sx = g % H_SX;
           const int cc = p.split ? sidx / KS : sidx;
           const int ky = p.split ? sidx - cc * KS : 0;
@@ -527,8 +540,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
       const int buf = NBUF == 2 ? (tcount & 1) : 0;
       const int use = NBUF == 2 ? (tcount >> 1) : tcount;
       int nt, ib, y0, x0;
-      item_origin(item, nt, ib, y0, x0);
-      const int mt = item - nt * m_items;
+      const int sp = item / items_per_split, it = item - sp * items_per_split;
+      item_origin(it, nt, ib, y0, x0);
+      const int mt = it - nt * m_items;
+      const bool raw = p.ws != nullptr;   // split-K: store the raw partial accumulators
       const float* bias_s = bias_all + nt * N;
       H_T0();
       mbar_wait(acc_full(buf), (uint32_t)(use & 1));
@@ -549,9 +564,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
         }
         const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
-        const bool has_add = p.addend != nullptr;
+        const bool has_add = p.addend != nullptr && !raw;
         const float* ap = has_add ? p.addend + (size_t)ob * p.a_bs + opix : p.y;
-        float* yp = p.y + (size_t)ob * p.y_bs + opix;
+        float* yp = raw ? p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix
+                        : p.y + (size_t)ob * p.y_bs + opix;
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 16) {
           const int nb = nt * N + c0;
@@ -577,7 +593,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float a = fmaf(__uint_as_float(r[j]), inv_scale, bs[j]);
-            val[j] = fmaf(leaky(a, slope), alpha, add[j]);
+            val[j] = raw ? __uint_as_float(r[j]) : fmaf(leaky(a, slope), alpha, add[j]);
           }
           if (m_ok) {
             if (nvalid == 16) {
@@ -954,6 +970,27 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ split-K finish
+// y = addend + alpha * act(inv_scale * sum_s ws[s] + bias): the partial sums are added in split order (deterministic).
+__global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_stride, int S, const uint8_t* __restrict__ wp,
+                                  const float* __restrict__ bias, const float* __restrict__ addend, long long a_bs,
+                                  float* __restrict__ y, long long y_bs, int Cout, int HWo, long long total, float slope,
+                                  float alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float inv_scale = __ldg(reinterpret_cast<const float*>(wp) + 1);
+  const int pix = (int)(i % HWo);
+  const long long r = i / HWo;
+  const int c = (int)(r % Cout);
+  const long long b = r / Cout;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += __ldg(ws + (size_t)s * ws_stride + i);
+  const float a = fmaf(acc, inv_scale, __ldg(bias + c));
+  const size_t o = (size_t)c * HWo + pix;
+  const float add = addend ? __ldg(addend + (size_t)b * a_bs + o) : 0.f;
+  y[(size_t)b * y_bs + o] = fmaf(leaky(a, slope), alpha, add);
+}
+
 // ------------------------------------------------------------------------------------------------ weight packer
 // Pass 1: max|w| of the layer -> header {max_abs, inv_scale, scale}, scale = 2^(14 - floor(log2(max))).
 __global__ void h16_scale_kernel(const float* __restrict__ w, float* __restrict__ hdr, long long n) {
@@ -1078,6 +1115,14 @@ static bool no_roll() {
   }
   return v == 1;
 }
+static bool no_splitk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRR_CONV_NO_SPLITK");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 static bool force_gather() {
   static int v = -1;
   if (v < 0) {
@@ -1087,9 +1132,46 @@ static bool force_gather() {
   return v == 1;
 }
 
+// Split-K plan: only when the layer has at most half as many tiles as the GPU has SMs and at least two K chunks.
+static int h16_ksplit(int base_items, int cchunks, int* cps_out) {
+  int ksplit = 1, cps = cchunks;
+  const int sms = sm_count();
+  if (cchunks >= 2 && base_items * 2 <= sms) {
+    int want = sms / base_items;
+    if (want > cchunks) want = cchunks;
+    cps = (cchunks + want - 1) / want;
+    ksplit = (cchunks + cps - 1) / cps;
+  }
+  *cps_out = cps;
+  return ksplit;
+}
+static void h16_staged_geom(int H, int W, int pad, int ks, int dil, int* rwl, int* ytiles, int* xtiles) {
+  int l = 4;
+  while ((1 << l) < W && l < 7) ++l;
+  const int RW = 1 << l, RH = 128 / RW;
+  (void)pad; (void)ks; (void)dil;
+  *rwl = l;
+  *ytiles = (H + 2 * RH - 1) / (2 * RH);
+  *xtiles = (W + RW - 1) / RW;
+}
+
+// Upper bound of the split-K workspace h16_conv may use for this shape (0 = the layer is never split).
+size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil) {
+  HGeom g = h_geom(Cout, Cin, ks);
+  const int pad = ((ks - 1) * dil) / 2;
+  const int Ho = (H + 2 * pad - dil * (ks - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
+  int rwl, yt, xt, cps;
+  h16_staged_geom(Ho, Wo, pad, ks, dil, &rwl, &yt, &xt);
+  const int items_staged = B * yt * xt * g.n_tiles;
+  const int items_gather = (int)(((long long)B * Ho * Wo + 255) / 256) * g.n_tiles;
+  const int k1 = h16_ksplit(items_staged, g.cchunks, &cps), k2 = h16_ksplit(items_gather, g.cchunks, &cps);
+  const int k = k1 > k2 ? k1 : k2;
+  return k > 1 ? (size_t)k * B * Cout * Ho * Wo * sizeof(float) : 0;
+}
+
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
              float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
-             float alpha, cudaStream_t st) {
+             float alpha, void* ws, size_t ws_bytes, cudaStream_t st) {
   HGeom g = h_geom(Cout, Cin, ks);
   HArgs a;
   memset(&a, 0, sizeof(a));
@@ -1143,8 +1225,8 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   if (staged) {
     // half = RH rows x RW columns, RW = smallest power of two >= W, clamped to [16, 128]
-    int rwl = 4;
-    while ((1 << rwl) < W && rwl < 7) ++rwl;
+    int rwl, yt_, xt_;
+    h16_staged_geom(a.Ho, a.Wo, a.pad, ks, dil, &rwl, &yt_, &xt_);
     const int RW = 1 << rwl, RH = 128 / RW;
     a.rw_log2 = rwl; a.rh = RH;
     a.split = (ks == 3 && dil > 1) ? 1 : 0;
@@ -1176,8 +1258,18 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
     a.m_items = (int)((a.M + 255) / 256);
   }
   a.items = a.m_items * g.n_tiles;
+  a.ksplit = 1; a.cps = g.cchunks; a.ws = nullptr; a.ws_stride = 0;
+  if (ws != nullptr && !no_splitk()) {
+    int cps;
+    const int k = h16_ksplit(a.items, g.cchunks, &cps);
+    const size_t slice = (size_t)B * Cout * a.Ho * a.Wo;
+    if (k > 1 && k * slice * sizeof(float) <= ws_bytes) {
+      a.ksplit = k; a.cps = cps; a.ws = reinterpret_cast<float*>(ws); a.ws_stride = (long long)slice;
+      a.items *= k;
+    }
+  }
   const size_t room = H_SMEM_MAX - x_bytes - misc;
-  a.resident = (g.n_tiles == 1 && total_b <= room) ? 1 : 0;
+  a.resident = (g.n_tiles == 1 && total_b <= room && a.ksplit == 1) ? 1 : 0;
   if (a.resident) {
     a.sb = 1;
     a.b_smem_bytes = (unsigned)total_b;
@@ -1194,8 +1286,14 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
     a.b_smem_bytes = (unsigned)((size_t)sb * g.img_bytes);
   }
   const size_t smem = (size_t)a.b_smem_bytes + x_bytes + misc;
-  if (staged) return ks == 1 ? launch_h16<1, true>(map, a, smem, st) : launch_h16<3, true>(map, a, smem, st);
-  return ks == 1 ? launch_h16<1, false>(map, a, smem, st) : launch_h16<3, false>(map, a, smem, st);
+  int rc;
+  if (staged) rc = ks == 1 ? launch_h16<1, true>(map, a, smem, st) : launch_h16<3, true>(map, a, smem, st);
+  else rc = ks == 1 ? launch_h16<1, false>(map, a, smem, st) : launch_h16<3, false>(map, a, smem, st);
+  if (rc != 0 || a.ksplit == 1) return rc;
+  const long long total = (long long)B * Cout * a.Ho * a.Wo;
+  h16_splitk_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.ws, a.ws_stride, a.ksplit, a.wp, bias, addend, a_bs, y,
+                                                                     y_bs, Cout, a.Ho * a.Wo, total, slope, alpha);
+  return check_launch("irr_conv2d_fwd");
 }
 
 }  // namespace irr

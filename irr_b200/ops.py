@@ -174,6 +174,9 @@ def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
     return packed
 
 
+_ws_bytes = {}
+
+
 def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, slope: float = 0.1, out=None,
            addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT):
     B, Cin, H, W = x.shape
@@ -185,9 +188,17 @@ def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, s
     pa, sa = (_v(addend, "addend") if addend is not None else (None, 0))
     if addend is not None:
         assert addend.shape == out.shape
-    _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), _lib.load().irr_conv2d_fwd, px, sx,
+    lib = _lib.load()
+    # split-K scratch for layers with far fewer tiles than SMs (coarse pyramid levels); 0 bytes = never split
+    key = (B, Cin, H, W, Cout, ks, stride, dil, math)
+    nws = _ws_bytes.get(key)
+    if nws is None:
+        nws = lib.irr_conv2d_workspace_bytes(B, Cin, H, W, Cout, ks, stride, dil, math)
+        _ws_bytes[key] = nws
+    ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
+    _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_ws, px, sx,
             packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, math,
-            _stream())
+            ws.data_ptr() if ws is not None else None, nws, _stream())
     return out
 
 
