@@ -121,6 +121,18 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
                       int stride, int dilation, float leaky_slope, float alpha, int math, void* workspace,
                       size_t workspace_bytes, irr_stream_t stream);
 
+/* Two layers that read the same input in one pass (IRR_MATH_TC_3XF16 only): output channels [0, n_split) get the
+ * first epilogue and go to y, channels [n_split, Cout) get (addend2, alpha2, leaky_slope2) and go to y2 (a
+ * B x (Cout - n_split) x Ho x Wo slice).  n_split must be a multiple of 16.  Used by the dense estimators
+ * (models/pwc_modules.py:163-170): conv_last(cat[conv5(x4), x4]) = W_last[:, :32] * conv5(x4) + W_last[:, 32:] * x4,
+ * so the 531/530-channel part of conv_last rides along with conv5 as extra output columns and only a 32-channel
+ * conv remains. */
+int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
+                        long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
+                        int stride, int dilation, float leaky_slope, float alpha, int n_split, const float* addend2,
+                        long long addend2_bs, float* y2, long long y2_bs, float leaky_slope2, float alpha2, int math,
+                        void* workspace, size_t workspace_bytes, irr_stream_t stream);
+
 /* A8 — upsample2d_as (models/pwc_modules.py:65-67): bilinear, align_corners=True, any in/out size, fused with an
  * optional per-channel-parity scale (even channels * scale_even, odd * scale_odd): rescale_flow of
  * pwc_modules.py:70-82 applied to the resized flow, or the final *(1/div_flow) of IRR_PWC.py:176. */

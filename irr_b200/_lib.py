@@ -38,6 +38,8 @@ PROTOTYPES = {
     "irr_conv2d_workspace_bytes": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i],
     "irr_conv2d_fwd_ws": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                           c_f, c_i, c_fp, C.c_size_t, c_fp],
+    "irr_conv2d_fwd_dual": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
+                            c_f, c_i, c_fp, c_ll, c_fp, c_ll, c_f, c_f, c_i, c_fp, C.c_size_t, c_fp],
     "irr_resize_bilinear_ac_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_fp],
     "irr_scale_channels_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_f, c_f, c_fp],
     "irr_upsample_nearest2x_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],

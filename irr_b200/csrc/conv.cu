@@ -16,9 +16,15 @@ int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, co
 bool tc_supported(int Cout, int Cin, int ks, int stride, int dil);
 size_t h16_packed_bytes(int Cout, int Cin, int ks);
 int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st);
+struct H16Dual {
+  int n_split;
+  float* y2; long long y2_bs;
+  const float* addend2; long long a2_bs;
+  float slope2, alpha2;
+};
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
              float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
-             float alpha, void* ws, size_t ws_bytes, cudaStream_t st);
+             float alpha, const H16Dual* dual, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil);
 }  // namespace irr
 
@@ -100,9 +106,32 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
       return IRR_E_UNSUPPORTED;
     }
     return h16_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
-                    leaky_slope, alpha, workspace, workspace_bytes, as_stream(stream));
+                    leaky_slope, alpha, nullptr, workspace, workspace_bytes, as_stream(stream));
   }
   return fail_arg(fn, "unknown math mode");
+}
+
+int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
+                        long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
+                        int stride, int dilation, float leaky_slope, float alpha, int n_split, const float* addend2,
+                        long long addend2_bs, float* y2, long long y2_bs, float leaky_slope2, float alpha2, int math,
+                        void* workspace, size_t workspace_bytes, irr_stream_t stream) {
+  const char* fn = "irr_conv2d_fwd_dual";
+  IRR_REQUIRE(x && w_packed && bias && y && y2, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
+  IRR_REQUIRE(ksize == 1 || ksize == 3, fn, "kernel_size must be 1 or 3");
+  IRR_REQUIRE(stride >= 1 && dilation >= 1, fn, "stride/dilation must be >= 1");
+  IRR_REQUIRE(math == IRR_MATH_TC_3XF16, fn, "dual output is implemented by the IRR_MATH_TC_3XF16 path only");
+  IRR_REQUIRE(n_split > 0 && n_split < Cout && (n_split % 16) == 0, fn, "n_split must be a multiple of 16 inside (0, Cout)");
+  IRR_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, fn, "w_packed must be 16-byte aligned");
+  if (!tc_supported(Cout, Cin, ksize, stride, dilation)) {
+    set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);
+    return IRR_E_UNSUPPORTED;
+  }
+  H16Dual d;
+  d.n_split = n_split; d.y2 = y2; d.y2_bs = y2_bs; d.addend2 = addend2; d.a2_bs = addend2_bs; d.slope2 = leaky_slope2; d.alpha2 = alpha2;
+  return h16_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
+                  leaky_slope, alpha, &d, workspace, workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

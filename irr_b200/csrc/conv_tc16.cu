@@ -62,8 +62,17 @@ struct HArgs {
   int rw_log2, rh, R, PW, padl, split, ytiles, xtiles, m_items, items;
   int ksplit, cps;            // split-K: K chunks are dealt to `ksplit` CTAs per tile, `cps` chunks each
   float* ws; long long ws_stride;  // split-K partial sums [ksplit][B][Cout][Ho*Wo] (raw accumulators)
+  // dual output: channels [n_split, Cout) go to y2 with their own epilogue (n_split % 16 == 0; == Cout when unused)
+  int n_split; float* y2; long long y2_bs; const float* addend2; long long a2_bs; float slope2, alpha2;
   long long M;
-  float slope, alpha;
+  float slope1, alpha1;
+};
+
+struct H16Dual {  // second destination for output channels [n_split, Cout)
+  int n_split;
+  float* y2; long long y2_bs;
+  const float* addend2; long long a2_bs;
+  float slope2, alpha2;
 };
 
 struct HGeom {
@@ -534,7 +543,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
     const int t = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int rin = t >> p.rw_log2, xin = t & (RW - 1);
-    const float slope = p.slope, alpha = p.alpha;
     int tcount = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
       const int buf = NBUF == 2 ? (tcount & 1) : 0;
@@ -564,20 +572,30 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
         }
         const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
-        const bool has_add = p.addend != nullptr && !raw;
-        const float* ap = has_add ? p.addend + (size_t)ob * p.a_bs + opix : p.y;
-        float* yp = raw ? p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix
-                        : p.y + (size_t)ob * p.y_bs + opix;
+        const float* ap1 = (p.addend != nullptr && !raw) ? p.addend + (size_t)ob * p.a_bs + opix : nullptr;
+        const float* ap2 = (p.addend2 != nullptr && !raw) ? p.addend2 + (size_t)ob * p.a2_bs + opix : nullptr;
+        float* yp1 = raw ? p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix
+                         : p.y + (size_t)ob * p.y_bs + opix;
+        float* yp2 = raw ? yp1 : (p.y2 != nullptr ? p.y2 + (size_t)ob * p.y2_bs + opix : yp1);
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 16) {
           const int nb = nt * N + c0;
           const int nvalid = min(16, p.Cout - nb);  // warp-uniform; < 16 only in the layer's last channel group
           if (nvalid <= 0) break;
+          // dual output (fused conv5 + conv_last tail of the dense estimators): groups past n_split use the second
+          // destination, residual and activation; raw split-K partials keep the single [Cout] layout
+          const bool sec = !raw && nb >= p.n_split;
+          const int cb = sec ? nb - p.n_split : nb;
+          const float* ap = sec ? ap2 : ap1;
+          const bool has_add = ap != nullptr;
+          float* yp = sec ? yp2 : yp1;
+          const float slope = sec ? p.slope2 : p.slope1;
+          const float alpha = sec ? p.alpha2 : p.alpha1;
           // residual / skip operand: 16 independent loads in flight before the accumulator is touched
           float add[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            add[j] = (has_add && m_ok && j < nvalid) ? __ldg(ap + (size_t)(nb + j) * HWo) : 0.f;
+            add[j] = (has_add && m_ok && j < nvalid) ? __ldg(ap + (size_t)(cb + j) * HWo) : 0.f;
           uint32_t r[16];
           H_ACC(1);
           h_tmem_ld16(acc_addr + (uint32_t)c0, r);
@@ -598,11 +616,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           if (m_ok) {
             if (nvalid == 16) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) yp[(size_t)(nb + j) * HWo] = val[j];
+              for (int j = 0; j < 16; ++j) yp[(size_t)(cb + j) * HWo] = val[j];
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < nvalid) yp[(size_t)(nb + j) * HWo] = val[j];
+                if (j < nvalid) yp[(size_t)(cb + j) * HWo] = val[j];
             }
           }
           H_ACC(3);
@@ -975,7 +993,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
 __global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_stride, int S, const uint8_t* __restrict__ wp,
                                   const float* __restrict__ bias, const float* __restrict__ addend, long long a_bs,
                                   float* __restrict__ y, long long y_bs, int Cout, int HWo, long long total, float slope,
-                                  float alpha) {
+                                  float alpha, int n_split, const float* __restrict__ addend2, long long a2_bs,
+                                  float* __restrict__ y2, long long y2_bs, float slope2, float alpha2) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float inv_scale = __ldg(reinterpret_cast<const float*>(wp) + 1);
@@ -986,9 +1005,15 @@ __global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_str
   float acc = 0.f;
   for (int s = 0; s < S; ++s) acc += __ldg(ws + (size_t)s * ws_stride + i);
   const float a = fmaf(acc, inv_scale, __ldg(bias + c));
-  const size_t o = (size_t)c * HWo + pix;
-  const float add = addend ? __ldg(addend + (size_t)b * a_bs + o) : 0.f;
-  y[(size_t)b * y_bs + o] = fmaf(leaky(a, slope), alpha, add);
+  if (c < n_split) {
+    const size_t o = (size_t)c * HWo + pix;
+    const float add = addend ? __ldg(addend + (size_t)b * a_bs + o) : 0.f;
+    y[(size_t)b * y_bs + o] = fmaf(leaky(a, slope), alpha, add);
+  } else {
+    const size_t o = (size_t)(c - n_split) * HWo + pix;
+    const float add = addend2 ? __ldg(addend2 + (size_t)b * a2_bs + o) : 0.f;
+    y2[(size_t)b * y2_bs + o] = fmaf(leaky(a, slope2), alpha2, add);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ weight packer
@@ -1171,7 +1196,7 @@ size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int s
 
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
              float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
-             float alpha, void* ws, size_t ws_bytes, cudaStream_t st) {
+             float alpha, const H16Dual* dual, void* ws, size_t ws_bytes, cudaStream_t st) {
   HGeom g = h_geom(Cout, Cin, ks);
   HArgs a;
   memset(&a, 0, sizeof(a));
@@ -1182,7 +1207,12 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   a.Wo = (W + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
   a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb;
   a.M = (long long)B * a.Ho * a.Wo;
-  a.slope = slope; a.alpha = alpha;
+  a.slope1 = slope; a.alpha1 = alpha;
+  a.n_split = Cout; a.y2 = nullptr; a.y2_bs = 0; a.addend2 = nullptr; a.a2_bs = 0; a.slope2 = 1.f; a.alpha2 = 1.f;
+  if (dual != nullptr && dual->n_split > 0 && dual->n_split < Cout) {
+    a.n_split = dual->n_split; a.y2 = dual->y2; a.y2_bs = dual->y2_bs; a.addend2 = dual->addend2; a.a2_bs = dual->a2_bs;
+    a.slope2 = dual->slope2; a.alpha2 = dual->alpha2;
+  }
   const size_t misc = 56 * 8 + 256 * 4 + 64;
   const size_t total_b = (size_t)g.nkb * g.img_bytes;
 
@@ -1192,7 +1222,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   // ---- rolling kernel: single-chunk thin layers on wide images
-  if (tma_ok && !no_roll() && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
+  if (tma_ok && !no_roll() && dual == nullptr && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
     RArgs r;
     memset(&r, 0, sizeof(r));
     r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
@@ -1292,7 +1322,9 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   if (rc != 0 || a.ksplit == 1) return rc;
   const long long total = (long long)B * Cout * a.Ho * a.Wo;
   h16_splitk_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.ws, a.ws_stride, a.ksplit, a.wp, bias, addend, a_bs, y,
-                                                                     y_bs, Cout, a.Ho * a.Wo, total, slope, alpha);
+                                                                     y_bs, Cout, a.Ho * a.Wo, total, slope, alpha,
+                                                                     a.n_split, a.addend2, a.a2_bs, a.y2 ? a.y2 : y, a.y2_bs,
+                                                                     a.slope2, a.alpha2);
   return check_launch("irr_conv2d_fwd");
 }
 

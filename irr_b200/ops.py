@@ -202,6 +202,30 @@ def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, s
     return out
 
 
+def conv2d_dual(x, packed, bias, Cout: int, n_split: int, ks: int, out, out2, stride: int = 1, dil: int = 1,
+                slope: float = 0.1, addend=None, alpha: float = 1.0, slope2: float = 1.0, addend2=None,
+                alpha2: float = 1.0, math: int = MATH_TC_3XF16):
+    """Two layers over the same input in one pass (include/irr_b200.h irr_conv2d_fwd_dual): channels [0, n_split) ->
+    ``out`` with (slope, addend, alpha); channels [n_split, Cout) -> ``out2`` with (slope2, addend2, alpha2)."""
+    B, Cin, H, W = x.shape
+    Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
+    assert out.shape == (B, n_split, Ho, Wo) and out2.shape == (B, Cout - n_split, Ho, Wo)
+    px, sx = _v(x, "x"); po, so = _v(out, "out"); po2, so2 = _v(out2, "out2")
+    pa, sa = (_v(addend, "addend") if addend is not None else (None, 0))
+    pa2, sa2 = (_v(addend2, "addend2") if addend2 is not None else (None, 0))
+    lib = _lib.load()
+    key = (B, Cin, H, W, Cout, ks, stride, dil, math)
+    nws = _ws_bytes.get(key)
+    if nws is None:
+        nws = lib.irr_conv2d_workspace_bytes(B, Cin, H, W, Cout, ks, stride, dil, math)
+        _ws_bytes[key] = nws
+    ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
+    _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_dual, px, sx,
+            packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, n_split,
+            pa2, sa2, po2, so2, slope2, alpha2, math, ws.data_ptr() if ws is not None else None, nws, _stream())
+    return out, out2
+
+
 def resize_ac(x, OH: int, OW: int, out=None, s_even: float = 1.0, s_odd: float = 1.0):
     B, C, H, W = x.shape
     if out is None:

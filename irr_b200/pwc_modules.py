@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from . import ops
 
-_default_math = ops.MATH_FP32_SIMT
+_default_math = ops.MATH_TC_3XF16  # the product path; MATH_FP32_SIMT / MATH_TC_3XTF32 remain selectable
 
 
 def set_conv_math(math: int) -> None:
@@ -163,10 +163,42 @@ class _DenseEstimator(nn.Module):
         """``buf``: (B, >= ch_in+448, H, W) whose channels [448 : 448+ch_in] already hold the block input.
         Fills channels [0:448]; returns conv_last(buf[:, :ch_in+448]) (+ addend) in ``out``."""
         hi = 448
+        fuse = get_conv_math() == ops.MATH_TC_3XF16
         for c, g in zip([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5], self.GROWTH):
+            if fuse and c is self.conv5:
+                break
             c(buf[:, hi:self.total_ch], out=buf[:, hi - g:hi])
             hi -= g
-        return self.conv_last(buf[:, 0:self.total_ch], out=out, addend=addend)
+        if not fuse:
+            return self.conv_last(buf[:, 0:self.total_ch], out=out, addend=addend)
+        # conv_last(cat[conv5(x4), x4]) = W_last[:, :32] * conv5(x4) + W_last[:, 32:] * x4 (+ b_last): the x4 part rides
+        # along with conv5 as extra output columns (one pass over the 531/530 channels instead of two), then a
+        # 32-channel conv adds the conv5 part.  Same sums, different association (<= 1e-6).
+        packed_f, bias_f, packed_l, zero_b = self._fused_tail()
+        B, _, H, W = buf.shape
+        co = self.ch_out
+        if out is None:
+            out = torch.empty((B, co, H, W), dtype=torch.float32, device=buf.device)
+        partial = torch.empty((B, co, H, W), dtype=torch.float32, device=buf.device)
+        ops.conv2d_dual(buf[:, 32:self.total_ch], packed_f, bias_f, 32 + co, 32, 3, out=buf[:, 0:32], out2=partial,
+                        slope=0.1, slope2=1.0, addend2=addend)
+        return ops.conv2d(buf[:, 0:32], packed_l, zero_b, co, 3, slope=1.0, out=out, addend=partial,
+                          math=ops.MATH_TC_3XF16)
+
+    def _fused_tail(self):
+        """Packed weights of the fused conv5 + conv_last tail (cached; rebuilt when a parameter changes)."""
+        w5, b5 = self.conv5[0].weight, self.conv5[0].bias
+        wl, bl = self.conv_last[0].weight, self.conv_last[0].bias
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in (w5, b5, wl, bl))
+        hit = getattr(self, "_fused_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                wf = torch.cat([w5, wl[:, 32:]], 0).contiguous()
+                bf = torch.cat([b5, bl], 0).contiguous()
+                hit = (key, (ops.pack_weights(wf, ops.MATH_TC_3XF16), bf,
+                             ops.pack_weights(wl[:, :32].contiguous(), ops.MATH_TC_3XF16), torch.zeros_like(bl)))
+            self._fused_cache = hit
+        return hit[1]
 
     def forward(self, x):
         B, C, H, W = x.shape

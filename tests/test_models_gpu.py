@@ -32,7 +32,7 @@ def conv_math(request):
     pwc_modules.set_conv_math({"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32,
                                "3xf16": ops.MATH_TC_3XF16}[request.param])
     yield request.param
-    pwc_modules.set_conv_math(ops.MATH_FP32_SIMT)
+    pwc_modules.set_conv_math(ops.MATH_TC_3XF16)
 
 
 @pytest.fixture(scope="module", params=[(128, 192), (94, 156)])

@@ -314,6 +314,28 @@ def test_conv2d_3xf16_rolling_slices_addend(cuda):
     assert (out[:, :7] == 0).all() and (out[:, 39:] == 0).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 531, 20, 64, 2), (1, 530, 7, 16, 1), (2, 115, 33, 39, 2)])
+def test_conv2d_3xf16_dual_output(cuda, shape):
+    """Fused conv5 + conv_last tail (irr_conv2d_fwd_dual) against two separate fp64 convs; includes a split-K shape and a
+    gather-variant shape."""
+    from irr_b200 import ops
+    B, Cin, H, W, co = shape
+    x = torch.from_numpy(rs(71, (B, Cin, H, W)))
+    w = torch.from_numpy(rs(72, (32 + co, Cin, 3, 3))) * float(np.sqrt(2.0 / (Cin * 9)))
+    b = torch.from_numpy(rs(73, (32 + co,))) * 0.1
+    add2 = torch.from_numpy(rs(74, (B, co, H, W)))
+    full = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+    ref1 = torch.nn.functional.leaky_relu(full[:, :32], 0.1)
+    ref2 = full[:, 32:] + add2.double()
+    out = torch.zeros((B, 40, H, W), device=cuda)
+    out2 = torch.empty((B, co, H, W), device=cuda)
+    ops.conv2d_dual(x.to(cuda), ops.pack_weights(w.to(cuda), ops.MATH_TC_3XF16), b.to(cuda), 32 + co, 32, 3,
+                    out=out[:, 3:35], out2=out2, slope=0.1, slope2=1.0, addend2=add2.to(cuda))
+    assert (out[:, 3:35].cpu().double() - ref1).abs().max().item() <= 1e-4
+    assert (out2.cpu().double() - ref2).abs().max().item() <= 1e-4
+    assert (out[:, :3] == 0).all() and (out[:, 35:] == 0).all()
+
+
 def test_conv2d_3xf16_slices_addend(cuda):
     from irr_b200 import ops
     B, Ct, H, W = 2, 100, 20, 36
