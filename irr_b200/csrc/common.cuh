@@ -1,5 +1,6 @@
 // Shared helpers for the irr_b200 kernels (sm_100a).  Internal header — the public ABI is include/irr_b200.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,6 +21,16 @@ int sm_count();
 
 static inline cudaStream_t as_stream(irr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cuTensorMapEncodeTiled, fetched at run time through cudaGetDriverEntryPoint (the library does not link libcuda);
+// nullptr when the driver does not provide it.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled();
+// fp32 NCHW channel-slice view (W, H, C, B; batch stride bs elements) -> tiled tensor map with the given box
+// (elements, innermost first).  Out-of-bounds box elements read as zero.  Needs W % 4 == 0, bs % 4 == 0, 16-byte base.
+bool make_nchw_map(CUtensorMap* map, const float* base, long long bs, int B, int C, int H, int W, int bw, int bh, int bc);
+
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -34,6 +45,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: 4-D tiled box load global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(

@@ -1079,22 +1079,7 @@ int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t 
 }
 
 // ------------------------------------------------------------------------------------------------ host launcher
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
+// encode_tiled() (cuTensorMapEncodeTiled fetched through the runtime, no libcuda link) lives in api.cu / common.cuh.
 
 template <int KS, bool STAGED, bool CTR>
 static int launch_h16_(const CUtensorMap& map, const HArgs& a, size_t smem, cudaStream_t st) {

@@ -22,6 +22,8 @@
 //     of cfg 3 is 28.6 MB), so DRAM traffic stays at the algorithmic B*H*W*(8C+324) bytes.
 //   * epilogue: / C, LeakyReLU, 16-byte stores into the caller's channel slice of the estimator input buffer.
 // No tensor cores by design (a 9x9-window dot product, not a GEMM).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace irr {
@@ -61,6 +63,128 @@ struct ProdPos {  // one halo (or f1) position owned by a producer thread
   int dx, dy;     // fused: +1 / +W when the second column / row is a distinct in-range texel, else 0
   float w00, w01, w10, w11;  // fused: bilinear weights with mask and bounds folded in; plain: w00 = 1 if in image else 0
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// COMPUTE role (warps 0-8 of either kernel): consumes the NS-slot ring of [f1 tile | f2 halo tile] chunks.
+template <int NS, bool PREFETCH>
+__device__ __forceinline__ void corr_compute(const float* smem, uint32_t full0, uint32_t empty0,
+                                             const float* __restrict__ f1, long long f1_bs,
+                                             const float* __restrict__ f2, long long f2_bs, float* __restrict__ out,
+                                             long long out_bs, int B, int C, int H, int W, int shift, float slope,
+                                             int vec_ok, int tiles_x, int tiles_y, int ntiles) {
+  const int tid = threadIdx.x;
+  const int HW = H * W;
+  const int nchunks = (C + CC - 1) / CC;
+  // Thread -> (tile row r, displacement row dyi, 8-pixel strip s8).  The 72 (r, dyi) pairs are dealt to the 9 warps
+  // sorted by the f2 halo row they read (h = r + dyi), 8 pairs x 4 strips per warp: a warp then touches only 2-4
+  // distinct f2 rows and ~5 f1 rows, and lanes that share a row and strip read the SAME 16 bytes — one shared-memory
+  // wavefront serves them all (broadcast).  With warp = dy (lane = row) every lane read its own 16 bytes and the
+  // 6 LDS.128 per channel cost 24 wavefronts per warp against 18 issue slots of FFMA: shared memory, not the FMA
+  // pipe, was the limiter.  Sorted, the same loads cost ~12 wavefronts.
+  const int lane = tid & 31;
+  const int s8 = lane & 3;
+  int r, dyi;
+  {
+    int p = (tid >> 5) * 8 + (lane >> 2), h = 0;  // p-th pair in (h, r) order; row h holds min(h, 15 - h) + 1 pairs
+    for (;;) {
+      const int cnt = (h < 8 ? h : 15 - h) + 1;
+      if (p < cnt) break;
+      p -= cnt;
+      ++h;
+    }
+    r = (h > 8 ? h - 8 : 0) + p;
+    dyi = h - r;  // 0..8 -> dy = dyi - 4
+  }
+  int gchunk = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int y0 = ty * TH, x0 = tx * TW;
+    float acc[ND][PX];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+#pragma unroll
+      for (int p = 0; p < PX; ++p) acc[d][p] = 0.f;
+
+    if (PREFETCH) {  // The compute warps spend most of a tile waiting on the producers: use them to pull the NEXT tile's f1 rows and
+       // (un-warped) f2 neighbourhood into L2, so the producers' gathers find their lines there instead of in DRAM.
+      const int ntile = tile + (int)gridDim.x;
+      if (ntile < ntiles) {
+        const int ntx = ntile % tiles_x, nty = (ntile / tiles_x) % tiles_y, nb = ntile / (tiles_x * tiles_y);
+        int nb2 = nb + shift;
+        if (nb2 >= B) nb2 -= B;
+        const float* pf1 = f1 + (size_t)nb * f1_bs;
+        const float* pf2 = f2 + (size_t)nb2 * f2_bs;
+        const int ny0 = nty * TH, nx0 = ntx * TW;
+        for (int i = tid; i < C * 40; i += NCOMP) {
+          const int c = i / 40, rr = i - c * 40;
+          const float* a;
+          if (rr < 8) {
+            const int y = min(ny0 + rr, H - 1);
+            a = pf1 + (size_t)c * HW + (size_t)y * W + min(nx0, W - 1);
+          } else {
+            const int k = rr - 8;
+            const int y = min(max(ny0 - MD + (k >> 1), 0), H - 1);
+            const int x = min(max(nx0 - MD + (k & 1) * 32, 0), W - 1);
+            a = pf2 + (size_t)c * HW + (size_t)y * W + x;
+          }
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+      }
+    }
+
+    for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+      const int s = gchunk % NS;
+      const uint32_t ph = (uint32_t)((gchunk / NS) & 1);
+      mbar_wait(full0 + 8u * s, ph);
+      const float* f1s = smem + s * STAGE_ELEMS;
+      const float* f2s = f1s + F1_ELEMS;
+#pragma unroll 2
+      for (int cc = 0; cc < CC; ++cc) {
+        const float4* ap = reinterpret_cast<const float4*>(f1s + (cc * TH + r) * F1_P + s8 * PX);
+        const float4* bp = reinterpret_cast<const float4*>(f2s + (cc * F2_H + r + dyi) * F2_P + s8 * PX);
+        float a[PX], bv[PX + 2 * MD];
+        float4 t0 = ap[0], t1 = ap[1];
+        a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 t = bp[q];
+          bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+#pragma unroll
+          for (int p = 0; p < PX; ++p) acc[d][p] = fmaf(a[p], bv[p + d], acc[d][p]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8u * s);
+    }
+
+    // ---- epilogue: mean over channels (pwc_modules.py:59 / .cu:107 divide by nelems), LeakyReLU (IRR_PWC.py:94-95)
+    const int gy = y0 + r;
+    const int gx = x0 + s8 * PX;
+    if (gy < H && gx < W) {
+      const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
+      float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        float v[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) v[p] = leaky(acc[d][p] * inv_c, slope);
+        float* q = op + (size_t)d * HW;
+        if (vec_ok && gx + PX <= W) {
+          reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);
+          reinterpret_cast<float4*>(q)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < PX; ++p)
+            if (gx + p < W) q[p] = v[p];
+        }
+      }
+    }
+  }
+}
 
 template <bool FUSED>
 __global__ void __launch_bounds__(CORR_THREADS, 1)
@@ -290,98 +414,258 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       gchunk += nchunks;
     }
   } else {
-    // ============================== COMPUTE ==============================
-    const int dyi = tid >> 5;  // 0..8  -> dy = dyi - 4
-    const int lane = tid & 31;
-    const int r = lane & 7, s8 = lane >> 3;
-    int gchunk = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    corr_compute<CORR_STAGES, true>(smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
+                                    vec_ok, tiles_x, tiles_y, ntiles);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed kernel (the default wherever rows are 16-byte aligned): same tiles, same compute warps, but the staging is
+// done by the copy engine.  One elected thread issues, per 8-channel chunk, a [8 ch][8 rows][36] box of f1 and — plain —
+// a [8][16][44] box of f2 straight into the ring slot (box origin (x0-4, y0-4): out-of-image rows / columns / channels
+// arrive as zeros, which IS the correlation's zero padding and the ragged channel tail; the extra 4 columns make the
+// row pitch bank-conflict-free).  No thread computes an address or a predicate per element any more.
+// Fused with the warp: the f2 box is the tile's 24 x 48 SOURCE FOOTPRINT, placed from the min/max of the sample
+// coordinates, delivered into a second ring; six SAMPLER warps turn footprint -> warped halo tile with the taps /
+// weights / hard mask they computed once per tile (for the NEXT tile while the current one is in flight, so the copy
+// engine never waits for them at a tile boundary).
+constexpr int T_NS_PLAIN = 6, T_NS_FUSED = 3, T_NFS = 3;
+constexpr int T_PLAIN_THREADS = NCOMP + 32;   // plain: 9 compute warps + the issuer's warp (no register cap at 128)
+constexpr int T_NSAMP = 192;                  // sampler threads (warps 10-15)
+constexpr int T_KPOS = (NHALO + T_NSAMP - 1) / T_NSAMP;  // 4 halo positions per sampler thread
+constexpr uint32_t T_F1_BYTES = F1_ELEMS * 4, T_F2_BYTES = F2_ELEMS * 4, T_FP_BYTES = FP_ELEMS * 4;
+constexpr int CORR_SMEM_TMA_PLAIN = T_NS_PLAIN * STAGE_ELEMS * 4 + 256;
+constexpr int CORR_SMEM_TMA_FUSED = T_NS_FUSED * STAGE_ELEMS * 4 + T_NFS * FP_ELEMS * 4 + 256;
+
+struct SampPos {      // one halo position owned by a sampler thread (valid for one tile)
+  int off;            // footprint-window offset of tap (y0,x0) (foot) / global offset y*W+x (gather); < 0 => dead
+  int dxy;            // bit 0: +1 column is a distinct texel, bit 1: +1 row is
+  float w00, w01, w10, w11;
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
+    corr_tma_kernel(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
+                    const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
+                    const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
+                    GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
+                    int ntiles) {
+  constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
+  extern __shared__ __align__(1024) float smem[];
+  float* fpr = smem + NS * STAGE_ELEMS;  // footprint ring (FUSED)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fpr + (FUSED ? T_NFS * FP_ELEMS : 0));
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (NS + s); };
+  auto fpfull = [&](int s) { return bar0 + 8u * (2 * NS + s); };
+  auto fpempty = [&](int s) { return bar0 + 8u * (2 * NS + T_NFS + s); };
+  auto metafull = [&](int s) { return bar0 + 8u * (2 * NS + 2 * T_NFS + s); };
+  int* meta = reinterpret_cast<int*>(bars + 2 * NS + 2 * T_NFS + 2);  // 2 x {oy, ox, foot, -}, then red[4]
+  int* red = meta + 8;
+
+  const int tid = threadIdx.x;
+  const int HW = H * W;
+  const int nchunks = (C + CC - 1) / CC;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(full(s), 1 + (FUSED ? T_NSAMP / 32 : 0));  // the copy's expect_tx arrival (+ one per sampler warp)
+      mbar_init(empty(s), NCOMP / 32);
+    }
+    for (int s = 0; s < T_NFS; ++s) {
+      mbar_init(fpfull(s), 1);
+      mbar_init(fpempty(s), T_NSAMP / 32);
+    }
+    mbar_init(metafull(0), 1);
+    mbar_init(metafull(1), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (tid < NCOMP) {
+    corr_compute<NS, false>(smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope, vec_ok,
+                            tiles_x, tiles_y, ntiles);
+  } else if (tid == NCOMP) {
+    // ============================== COPY ISSUER (one thread) ==============================
+    int gchunk = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
       const int b = tile / (tiles_x * tiles_y);
       const int y0 = ty * TH, x0 = tx * TW;
-      float acc[ND][PX];
-#pragma unroll
-      for (int d = 0; d < ND; ++d)
-#pragma unroll
-        for (int p = 0; p < PX; ++p) acc[d][p] = 0.f;
-
-      {  // The compute warps spend most of a tile waiting on the producers: use them to pull the NEXT tile's f1 rows and
-         // (un-warped) f2 neighbourhood into L2, so the producers' gathers find their lines there instead of in DRAM.
-        const int ntile = tile + (int)gridDim.x;
-        if (ntile < ntiles) {
-          const int ntx = ntile % tiles_x, nty = (ntile / tiles_x) % tiles_y, nb = ntile / (tiles_x * tiles_y);
-          int nb2 = nb + shift;
-          if (nb2 >= B) nb2 -= B;
-          const float* pf1 = f1 + (size_t)nb * f1_bs;
-          const float* pf2 = f2 + (size_t)nb2 * f2_bs;
-          const int ny0 = nty * TH, nx0 = ntx * TW;
-          for (int i = tid; i < C * 40; i += NCOMP) {
-            const int c = i / 40, rr = i - c * 40;
-            const float* a;
-            if (rr < 8) {
-              const int y = min(ny0 + rr, H - 1);
-              a = pf1 + (size_t)c * HW + (size_t)y * W + min(nx0, W - 1);
-            } else {
-              const int k = rr - 8;
-              const int y = min(max(ny0 - MD + (k >> 1), 0), H - 1);
-              const int x = min(max(nx0 - MD + (k & 1) * 32, 0), W - 1);
-              a = pf2 + (size_t)c * HW + (size_t)y * W + x;
-            }
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      int b2 = b + shift;
+      if (b2 >= B) b2 -= B;
+      int oy = 0, ox = 0, foot = 0;
+      if (FUSED) {
+        mbar_wait(metafull(it & 1), (uint32_t)((it >> 1) & 1));
+        const volatile int* mt = meta + 4 * (it & 1);
+        oy = mt[0]; ox = mt[1]; foot = mt[2];
+      }
+      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+        const int s = gchunk % NS;
+        mbar_wait(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1));
+        const uint32_t st = smem_u32(smem + s * STAGE_ELEMS);
+        if (!FUSED) {
+          mbar_expect_tx(full(s), T_F1_BYTES + T_F2_BYTES);
+          tma_load_4d(st, &m1, x0, y0, ci * CC, b, full(s));
+          tma_load_4d(st + T_F1_BYTES, &m2, x0 - MD, y0 - MD, ci * CC, b2, full(s));
+        } else {
+          mbar_expect_tx(full(s), T_F1_BYTES);
+          tma_load_4d(st, &m1, x0, y0, ci * CC, b, full(s));
+          const int fs = gchunk % T_NFS;
+          mbar_wait(fpempty(fs), (uint32_t)(((gchunk / T_NFS) & 1) ^ 1));
+          if (foot) {
+            mbar_expect_tx(fpfull(fs), T_FP_BYTES);
+            tma_load_4d(smem_u32(fpr + fs * FP_ELEMS), &m2, ox, oy, ci * CC, b2, fpfull(fs));
+          } else {
+            mbar_arrive(fpfull(fs));  // divergent tile: the samplers gather from global memory, keep the phases moving
           }
         }
       }
-
-      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
-        const int s = gchunk % CORR_STAGES;
-        const uint32_t ph = (uint32_t)((gchunk / CORR_STAGES) & 1);
-        mbar_wait(full(s), ph);
-        const float* f1s = smem + s * STAGE_ELEMS;
-        const float* f2s = f1s + F1_ELEMS;
-#pragma unroll 2
-        for (int cc = 0; cc < CC; ++cc) {
-          const float4* ap = reinterpret_cast<const float4*>(f1s + (cc * TH + r) * F1_P + s8 * PX);
-          const float4* bp = reinterpret_cast<const float4*>(f2s + (cc * F2_H + r + dyi) * F2_P + s8 * PX);
-          float a[PX], bv[PX + 2 * MD];
-          float4 t0 = ap[0], t1 = ap[1];
-          a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+    }
+  } else if (FUSED && tid >= CORR_THREADS - T_NSAMP) {
+    // ============================== SAMPLERS (warps 10-15) ==============================
+    const int pt = tid - (CORR_THREADS - T_NSAMP);
+    const int lane = tid & 31;
+    auto samp_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T_NSAMP) : "memory"); };
+    // per-tile setup: taps of the <= 4 halo positions this thread owns, footprint placement, publication to the issuer
+    auto setup = [&](int tile, int slot, SampPos* sp, int& foot_out) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int y0 = ty * TH, x0 = tx * TW;
+      int ya_[T_KPOS], xa_[T_KPOS];
+      int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 t = bp[q];
-            bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+      for (int k = 0; k < T_KPOS; ++k) {
+        const int h = pt + k * T_NSAMP;
+        SampPos q;
+        q.off = -1; q.dxy = 0; q.w00 = q.w01 = q.w10 = q.w11 = 0.f;
+        ya_[k] = 0; xa_[k] = 0;
+        if (h < NHALO) {
+          const int hr = h / F2_WV, hx = h - hr * F2_WV;
+          const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * W + gx;
+            float ix, iy;
+            sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
+            Taps tp = make_taps(ix, iy, W, H);
+            if (tp.mask != 0.f && (tp.w00 != 0.f || tp.w01 != 0.f || tp.w10 != 0.f || tp.w11 != 0.f)) {
+              const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
+              const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
+              ya_[k] = ya; xa_[k] = xa;
+              q.off = 0;
+              q.dxy = ((xb != xa) ? 1 : 0) | ((yb != ya) ? 2 : 0);
+              // a clamped (out-of-range) tap has zero weight (make_taps): aliasing it onto its in-range neighbour's
+              // address is harmless, the four reads are always in bounds.
+              q.w00 = tp.w00; q.w01 = tp.w01; q.w10 = tp.w10; q.w11 = tp.w11;
+              lo_y = min(lo_y, ya); hi_y = max(hi_y, yb); lo_x = min(lo_x, xa); hi_x = max(hi_x, xb);
+            }
           }
+        }
+        sp[k] = q;
+      }
+      if (pt == 0) { red[0] = 1 << 30; red[1] = -1; red[2] = 1 << 30; red[3] = -1; }
+      samp_sync();
 #pragma unroll
-          for (int d = 0; d < ND; ++d)
+      for (int o = 16; o > 0; o >>= 1) {
+        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+      }
+      if (lane == 0) { atomicMin(&red[0], lo_y); atomicMax(&red[1], hi_y); atomicMin(&red[2], lo_x); atomicMax(&red[3], hi_x); }
+      samp_sync();
+      const int ymin = red[0], ymax = red[1], xmin = red[2], xmax = red[3];
+      const bool any_live = ymax >= ymin;
+      const int oy = any_live ? ymin : 0, ox = any_live ? (xmin & ~3) : 0;  // TMA traps on an inner coordinate that is not 16-byte aligned (measured)
+      const int foot = (!any_live || ((ymax - oy) < FP_H && (xmax - ox) < FP_W)) ? 1 : 0;
 #pragma unroll
-            for (int p = 0; p < PX; ++p) acc[d][p] = fmaf(a[p], bv[p + d], acc[d][p]);
+      for (int k = 0; k < T_KPOS; ++k)
+        if (sp[k].off >= 0) sp[k].off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * W + xa_[k];
+      samp_sync();  // red[] is re-initialised by the next setup
+      if (pt == 0) {
+        int* mt = meta + 4 * slot;
+        mt[0] = oy; mt[1] = ox; mt[2] = foot;
+        mbar_arrive(metafull(slot));  // release: the issuer's wait acquires the three words
+      }
+      foot_out = foot;
+    };
+
+    SampPos cur[T_KPOS], nxt[T_KPOS];
+    int foot = 0, foot_n = 0, gchunk = 0, it = 0;
+    if ((int)blockIdx.x < ntiles) setup(blockIdx.x, 0, cur, foot);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = tile / (tiles_x * tiles_y);
+      int b2 = b + shift;
+      if (b2 >= B) b2 -= B;
+      const float* f2b = f2 + (size_t)b2 * f2_bs;
+      const int ntile = tile + (int)gridDim.x;
+      if (ntile < ntiles) setup(ntile, (it + 1) & 1, nxt, foot_n);
+      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+        const int s = gchunk % NS, fs = gchunk % T_NFS;
+        mbar_wait(fpfull(fs), (uint32_t)((gchunk / T_NFS) & 1));
+        mbar_wait(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1));
+        float* st = smem + s * STAGE_ELEMS + F1_ELEMS;
+        const int c0 = ci * CC;
+        if (foot) {
+          const float* fp = fpr + fs * FP_ELEMS;
+#pragma unroll
+          for (int k = 0; k < T_KPOS; ++k) {
+            const int h = pt + k * T_NSAMP;
+            if (h < NHALO) {
+              const int hr = h / F2_WV, hx = h - hr * F2_WV;
+              float* dst = st + hr * F2_P + hx;
+              const bool live = cur[k].off >= 0;
+              const float* pq = fp + (live ? cur[k].off : 0);
+              const int dx = cur[k].dxy & 1, dy = (cur[k].dxy & 2) ? FP_W : 0;
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) {
+                const float* pc = pq + cc * (FP_H * FP_W);
+                float a = __fmul_rn(pc[0], cur[k].w00);  // tap order of grid_sampler_2d
+                a = fmaf(pc[dx], cur[k].w01, a);
+                a = fmaf(pc[dy], cur[k].w10, a);
+                a = fmaf(pc[dy + dx], cur[k].w11, a);
+                dst[cc * (F2_H * F2_P)] = live ? a : 0.f;
+              }
+            }
+          }
+        } else {  // divergent flow: gather the taps from global memory
+#pragma unroll
+          for (int k = 0; k < T_KPOS; ++k) {
+            const int h = pt + k * T_NSAMP;
+            if (h < NHALO) {
+              const int hr = h / F2_WV, hx = h - hr * F2_WV;
+              float* dst = st + hr * F2_P + hx;
+              const bool live = cur[k].off >= 0;
+              const float* pq = f2b + (size_t)c0 * HW + (live ? cur[k].off : 0);
+              const int dx = cur[k].dxy & 1, dy = (cur[k].dxy & 2) ? W : 0;
+              float t[4][CC];
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) {
+                const bool okc = live && (c0 + cc < C);
+                const float* pc = pq + (size_t)cc * HW;
+                t[0][cc] = okc ? __ldg(pc) : 0.f;
+                t[1][cc] = okc ? __ldg(pc + dx) : 0.f;
+                t[2][cc] = okc ? __ldg(pc + dy) : 0.f;
+                t[3][cc] = okc ? __ldg(pc + dy + dx) : 0.f;
+              }
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) {
+                float a = __fmul_rn(t[0][cc], cur[k].w00);
+                a = fmaf(t[1][cc], cur[k].w01, a);
+                a = fmaf(t[2][cc], cur[k].w10, a);
+                dst[cc * (F2_H * F2_P)] = fmaf(t[3][cc], cur[k].w11, a);
+              }
+            }
+          }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty(s));
-      }
-
-      // ---- epilogue: mean over channels (pwc_modules.py:59 / .cu:107 divide by nelems), LeakyReLU (IRR_PWC.py:94-95)
-      const int gy = y0 + r;
-      const int gx = x0 + s8 * PX;
-      if (gy < H && gx < W) {
-        const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
-        float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          float v[PX];
-#pragma unroll
-          for (int p = 0; p < PX; ++p) v[p] = leaky(acc[d][p] * inv_c, slope);
-          float* q = op + (size_t)d * HW;
-          if (vec_ok && gx + PX <= W) {
-            reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);
-            reinterpret_cast<float4*>(q)[1] = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-#pragma unroll
-            for (int p = 0; p < PX; ++p)
-              if (gx + p < W) q[p] = v[p];
-          }
+        if (lane == 0) {
+          mbar_arrive(full(s));
+          mbar_arrive(fpempty(fs));
         }
       }
+#pragma unroll
+      for (int k = 0; k < T_KPOS; ++k) cur[k] = nxt[k];
+      foot = foot_n;
     }
   }
 }
@@ -417,6 +701,11 @@ __global__ void corr_generic_kernel(const float* __restrict__ in1, const float* 
   out[i] = acc / (float)(ks * ks * C);
 }
 
+static bool corr_no_tma() {  // IRR_CORR_NO_TMA=1: force the cp.async kernel (A/B measurements, tests of the fallback)
+  const char* e = getenv("IRR_CORR_NO_TMA");
+  return e && e[0] == '1';
+}
+
 template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
@@ -440,6 +729,25 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   if (nt > 0x7fffffffLL) return fail_arg(fn, "too many tiles");
   int ntiles = (int)nt;
   int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
+  if (vec_in && !corr_no_tma()) {
+    constexpr int TSMEM = FUSED ? CORR_SMEM_TMA_FUSED : CORR_SMEM_TMA_PLAIN;
+    static bool tattr_done = false;
+    CUtensorMap m1, m2;
+    if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC) &&
+        make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC)) {
+      if (!tattr_done) {
+        cudaError_t e = cudaFuncSetAttribute(corr_tma_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM);
+        if (e != cudaSuccess) {
+          set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+          return (int)e;
+        }
+        tattr_done = true;
+      }
+      corr_tma_kernel<FUSED><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g,
+                                                                B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles);
+      return check_launch(fn);
+    }
+  }
   corr_kernel<FUSED><<<grid, CORR_THREADS, CORR_SMEM, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H,
                                                             W, shift, slope, vec_ok, vec_in, tiles_x, tiles_y, ntiles);
   return check_launch(fn);
