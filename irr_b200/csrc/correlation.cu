@@ -66,8 +66,12 @@ struct ProdPos {  // one halo (or f1) position owned by a producer thread
 
 // ---------------------------------------------------------------------------------------------------------
 // COMPUTE role (warps 0-8 of either kernel): consumes the NS-slot ring of [f1 tile | f2 halo tile] chunks.
-template <int NS, bool PREFETCH>
-__device__ __forceinline__ void corr_compute(const float* smem, uint32_t full0, uint32_t empty0,
+struct NoTileHook {
+  __device__ __forceinline__ void setup(int, int) const {}
+};
+
+template <int NS, bool PREFETCH, class Hook>
+__device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem, uint32_t full0, uint32_t empty0,
                                              const float* __restrict__ f1, long long f1_bs,
                                              const float* __restrict__ f2, long long f2_bs, float* __restrict__ out,
                                              long long out_bs, int B, int C, int H, int W, int shift, float slope,
@@ -95,12 +99,14 @@ __device__ __forceinline__ void corr_compute(const float* smem, uint32_t full0, 
     r = (h > 8 ? h - 8 : 0) + p;
     dyi = h - r;  // 0..8 -> dy = dyi - 4
   }
-  int gchunk = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int gchunk = 0, it = 0;
+  if ((int)blockIdx.x < ntiles) hook.setup(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int tx = tile % tiles_x;
     const int ty = (tile / tiles_x) % tiles_y;
     const int b = tile / (tiles_x * tiles_y);
     const int y0 = ty * TH, x0 = tx * TW;
+    if (tile + (int)gridDim.x < ntiles) hook.setup(tile + (int)gridDim.x, it + 1);  // accumulators are dead here
     float acc[ND][PX];
 #pragma unroll
     for (int d = 0; d < ND; ++d)
@@ -167,20 +173,25 @@ __device__ __forceinline__ void corr_compute(const float* smem, uint32_t full0, 
     if (gy < H && gx < W) {
       const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
       float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
+      // scale in place first, then issue the 18 stores back to back (a temporary per displacement makes every store
+      // wait for the previous one to release its registers)
 #pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        float v[PX];
+      for (int d = 0; d < ND; ++d)
 #pragma unroll
-        for (int p = 0; p < PX; ++p) v[p] = leaky(acc[d][p] * inv_c, slope);
-        float* q = op + (size_t)d * HW;
-        if (vec_ok && gx + PX <= W) {
-          reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);
-          reinterpret_cast<float4*>(q)[1] = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
+        for (int p = 0; p < PX; ++p) acc[d][p] = leaky(acc[d][p] * inv_c, slope);
+      if (vec_ok && gx + PX <= W) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          float4* q = reinterpret_cast<float4*>(op + (size_t)d * HW);
+          q[0] = make_float4(acc[d][0], acc[d][1], acc[d][2], acc[d][3]);
+          q[1] = make_float4(acc[d][4], acc[d][5], acc[d][6], acc[d][7]);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
 #pragma unroll
           for (int p = 0; p < PX; ++p)
-            if (gx + p < W) q[p] = v[p];
-        }
+            if (gx + p < W) op[(size_t)d * HW + p] = acc[d][p];
       }
     }
   }
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       gchunk += nchunks;
     }
   } else {
-    corr_compute<CORR_STAGES, true>(smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
+    corr_compute<CORR_STAGES, true>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
                                     vec_ok, tiles_x, tiles_y, ntiles);
   }
 }
@@ -426,21 +437,110 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
 // arrive as zeros, which IS the correlation's zero padding and the ragged channel tail; the extra 4 columns make the
 // row pitch bank-conflict-free).  No thread computes an address or a predicate per element any more.
 // Fused with the warp: the f2 box is the tile's 24 x 48 SOURCE FOOTPRINT, placed from the min/max of the sample
-// coordinates, delivered into a second ring; six SAMPLER warps turn footprint -> warped halo tile with the taps /
-// weights / hard mask they computed once per tile (for the NEXT tile while the current one is in flight, so the copy
-// engine never waits for them at a tile boundary).
-constexpr int T_NS_PLAIN = 6, T_NS_FUSED = 3, T_NFS = 3;
+// coordinates, delivered into a second ring; six SAMPLER warps turn footprint -> warped halo tile.  The taps / weights
+// / hard mask of a tile's 640 halo positions (bit-exact recipe, common.cuh) are computed ONE TILE AHEAD by the compute
+// warps — at the one point where their 72 accumulators are dead and they would otherwise wait for the samplers — into
+// a double-buffered shared-memory table; the samplers and the copy issuer only read it (ncu: with the set-up on the
+// sampler warps it was 48 % of their time and the compute warps waited 43 % of theirs).
+constexpr int T_NS_PLAIN = 6, T_NS_FUSED = 3, T_NFS = 2;
 constexpr int T_PLAIN_THREADS = NCOMP + 32;   // plain: 9 compute warps + the issuer's warp (no register cap at 128)
 constexpr int T_NSAMP = 192;                  // sampler threads (warps 10-15)
 constexpr int T_KPOS = (NHALO + T_NSAMP - 1) / T_NSAMP;  // 4 halo positions per sampler thread
+constexpr int T_KSET = (NHALO + NCOMP - 1) / NCOMP;      // 3 halo positions per compute thread in the set-up
 constexpr uint32_t T_F1_BYTES = F1_ELEMS * 4, T_F2_BYTES = F2_ELEMS * 4, T_FP_BYTES = FP_ELEMS * 4;
+constexpr int T_TAB_WORDS = NHALO * 5;        // per slot: float4 weights[640], int off_dxy[640]
 constexpr int CORR_SMEM_TMA_PLAIN = T_NS_PLAIN * STAGE_ELEMS * 4 + 256;
-constexpr int CORR_SMEM_TMA_FUSED = T_NS_FUSED * STAGE_ELEMS * 4 + T_NFS * FP_ELEMS * 4 + 256;
+constexpr int CORR_SMEM_TMA_FUSED = T_NS_FUSED * STAGE_ELEMS * 4 + T_NFS * FP_ELEMS * 4 + 2 * T_TAB_WORDS * 4 + 256;
 
-struct SampPos {      // one halo position owned by a sampler thread (valid for one tile)
-  int off;            // footprint-window offset of tap (y0,x0) (foot) / global offset y*W+x (gather); < 0 => dead
-  int dxy;            // bit 0: +1 column is a distinct texel, bit 1: +1 row is
-  float w00, w01, w10, w11;
+// Tap table set-up for one tile (runs on the 288 compute threads, one tile ahead).
+struct TapSetup {
+  const float* flow; long long flow_bs;
+  GridArgs g;
+  int H, W, tiles_x, tiles_y;
+  float* tab;      // [2][T_TAB_WORDS]
+  int* meta;       // [2][4] {oy, ox, foot, -}
+  int* red;        // [3][4] {ymin, ymax, xmin, xmax}
+  uint32_t tabfull0;
+  __device__ __forceinline__ void setup(int tile, int j) const {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int HW = H * W;
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int y0 = ty * TH, x0 = tx * TW;
+    const int slot = j & 1;
+    int* rd = red + 4 * (j % 3);
+    if (tid == 0) {  // the slot of the NEXT reduction; nobody touches it before the barrier below
+      int* rn = red + 4 * ((j + 1) % 3);
+      rn[0] = 1 << 30; rn[1] = -1; rn[2] = 1 << 30; rn[3] = -1;
+    }
+    float fu[T_KSET], fv[T_KSET];
+    bool in_[T_KSET];
+#pragma unroll
+    for (int k = 0; k < T_KSET; ++k) {  // all flow loads in flight before any arithmetic
+      const int h = tid + k * NCOMP;
+      const int hr = h / F2_WV, hx = h - hr * F2_WV;
+      const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+      in_[k] = h < NHALO && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* fl = flow + (size_t)b * flow_bs + (in_[k] ? (size_t)gy * W + gx : 0);
+      fu[k] = __ldg(fl); fv[k] = __ldg(fl + HW);
+    }
+    float4 wq[T_KSET];
+    int ya_[T_KSET], xa_[T_KSET], dxy[T_KSET];
+    int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
+#pragma unroll
+    for (int k = 0; k < T_KSET; ++k) {
+      const int h = tid + k * NCOMP;
+      wq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ya_[k] = 0; xa_[k] = 0; dxy[k] = -1;  // dead
+      if (in_[k]) {
+        const int hr = h / F2_WV, hx = h - hr * F2_WV;
+        const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+        float ix, iy;
+        sample_coords(g, fu[k], fv[k], gx, gy, W, H, ix, iy);
+        Taps tp = make_taps(ix, iy, W, H);
+        if (tp.mask != 0.f && (tp.w00 != 0.f || tp.w01 != 0.f || tp.w10 != 0.f || tp.w11 != 0.f)) {
+          const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
+          const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
+          ya_[k] = ya; xa_[k] = xa;
+          // a clamped (out-of-range) tap has zero weight (make_taps): aliasing it onto its in-range neighbour's
+          // address is harmless, the four reads are always in bounds.
+          dxy[k] = ((xb != xa) ? 1 : 0) | ((yb != ya) ? 2 : 0);
+          wq[k] = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
+          lo_y = min(lo_y, ya); hi_y = max(hi_y, yb); lo_x = min(lo_x, xa); hi_x = max(hi_x, xb);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+      lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+    }
+    if (lane == 0 && hi_y >= 0) { atomicMin(&rd[0], lo_y); atomicMax(&rd[1], hi_y); atomicMin(&rd[2], lo_x); atomicMax(&rd[3], hi_x); }
+    asm volatile("bar.sync 2, %0;" ::"n"(NCOMP) : "memory");
+    const int ymin = rd[0], ymax = rd[1], xmin = rd[2], xmax = rd[3];
+    const bool any_live = ymax >= ymin;
+    // TMA traps on an inner coordinate that is not 16-byte aligned (measured): align the window origin down
+    const int oy = any_live ? ymin : 0, ox = any_live ? (xmin & ~3) : 0;
+    const int foot = (!any_live || ((ymax - oy) < FP_H && (xmax - ox) < FP_W)) ? 1 : 0;
+    float4* tw = reinterpret_cast<float4*>(tab + slot * T_TAB_WORDS);
+    int* to = reinterpret_cast<int*>(tab + slot * T_TAB_WORDS + NHALO * 4);
+#pragma unroll
+    for (int k = 0; k < T_KSET; ++k) {
+      const int h = tid + k * NCOMP;
+      if (h < NHALO) {
+        tw[h] = wq[k];
+        const int off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * W + xa_[k];
+        to[h] = dxy[k] < 0 ? -1 : ((off << 2) | dxy[k]);
+      }
+    }
+    if (tid == 0) {
+      int* mt = meta + 4 * slot;
+      mt[0] = oy; mt[1] = ox; mt[2] = foot;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tabfull0 + 8u * slot);  // release: readers acquire the table and meta through the wait
+  }
 };
 
 template <bool FUSED>
@@ -452,15 +552,16 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
                     int ntiles) {
   constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
   extern __shared__ __align__(1024) float smem[];
-  float* fpr = smem + NS * STAGE_ELEMS;  // footprint ring (FUSED)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fpr + (FUSED ? T_NFS * FP_ELEMS : 0));
+  float* fpr = smem + NS * STAGE_ELEMS;                          // footprint ring (FUSED)
+  float* tab = fpr + (FUSED ? T_NFS * FP_ELEMS : 0);             // tap tables (FUSED)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + (FUSED ? 2 * T_TAB_WORDS : 0));
   const uint32_t bar0 = smem_u32(bars);
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (NS + s); };
   auto fpfull = [&](int s) { return bar0 + 8u * (2 * NS + s); };
   auto fpempty = [&](int s) { return bar0 + 8u * (2 * NS + T_NFS + s); };
-  auto metafull = [&](int s) { return bar0 + 8u * (2 * NS + 2 * T_NFS + s); };
-  int* meta = reinterpret_cast<int*>(bars + 2 * NS + 2 * T_NFS + 2);  // 2 x {oy, ox, foot, -}, then red[4]
+  auto tabfull = [&](int s) { return bar0 + 8u * (2 * NS + 2 * T_NFS + s); };
+  int* meta = reinterpret_cast<int*>(bars + 2 * NS + 2 * T_NFS + 2);  // 2 x {oy, ox, foot, -}, then red[3][4]
   int* red = meta + 8;
 
   const int tid = threadIdx.x;
@@ -475,15 +576,24 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       mbar_init(fpfull(s), 1);
       mbar_init(fpempty(s), T_NSAMP / 32);
     }
-    mbar_init(metafull(0), 1);
-    mbar_init(metafull(1), 1);
+    mbar_init(tabfull(0), NCOMP / 32);
+    mbar_init(tabfull(1), NCOMP / 32);
+    for (int i = 0; i < 3; ++i) { red[4 * i] = 1 << 30; red[4 * i + 1] = -1; red[4 * i + 2] = 1 << 30; red[4 * i + 3] = -1; }
     mbar_fence_init();
   }
   __syncthreads();
 
   if (tid < NCOMP) {
-    corr_compute<NS, false>(smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope, vec_ok,
-                            tiles_x, tiles_y, ntiles);
+    if (FUSED) {
+      TapSetup hook;
+      hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.tiles_x = tiles_x;
+      hook.tiles_y = tiles_y; hook.tab = tab; hook.meta = meta; hook.red = red; hook.tabfull0 = tabfull(0);
+      corr_compute<NS, false>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
+                              vec_ok, tiles_x, tiles_y, ntiles);
+    } else {
+      corr_compute<NS, false>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift,
+                              slope, vec_ok, tiles_x, tiles_y, ntiles);
+    }
   } else if (tid == NCOMP) {
     // ============================== COPY ISSUER (one thread) ==============================
     int gchunk = 0, it = 0;
@@ -496,7 +606,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       if (b2 >= B) b2 -= B;
       int oy = 0, ox = 0, foot = 0;
       if (FUSED) {
-        mbar_wait(metafull(it & 1), (uint32_t)((it >> 1) & 1));
+        mbar_wait(tabfull(it & 1), (uint32_t)((it >> 1) & 1));
         const volatile int* mt = meta + 4 * (it & 1);
         oy = mt[0]; ox = mt[1]; foot = mt[2];
       }
@@ -526,79 +636,28 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     // ============================== SAMPLERS (warps 10-15) ==============================
     const int pt = tid - (CORR_THREADS - T_NSAMP);
     const int lane = tid & 31;
-    auto samp_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T_NSAMP) : "memory"); };
-    // per-tile setup: taps of the <= 4 halo positions this thread owns, footprint placement, publication to the issuer
-    auto setup = [&](int tile, int slot, SampPos* sp, int& foot_out) {
-      const int tx = tile % tiles_x;
-      const int ty = (tile / tiles_x) % tiles_y;
-      const int b = tile / (tiles_x * tiles_y);
-      const int y0 = ty * TH, x0 = tx * TW;
-      int ya_[T_KPOS], xa_[T_KPOS];
-      int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
-#pragma unroll
-      for (int k = 0; k < T_KPOS; ++k) {
-        const int h = pt + k * T_NSAMP;
-        SampPos q;
-        q.off = -1; q.dxy = 0; q.w00 = q.w01 = q.w10 = q.w11 = 0.f;
-        ya_[k] = 0; xa_[k] = 0;
-        if (h < NHALO) {
-          const int hr = h / F2_WV, hx = h - hr * F2_WV;
-          const int gy = y0 - MD + hr, gx = x0 - MD + hx;
-          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * W + gx;
-            float ix, iy;
-            sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
-            Taps tp = make_taps(ix, iy, W, H);
-            if (tp.mask != 0.f && (tp.w00 != 0.f || tp.w01 != 0.f || tp.w10 != 0.f || tp.w11 != 0.f)) {
-              const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
-              const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
-              ya_[k] = ya; xa_[k] = xa;
-              q.off = 0;
-              q.dxy = ((xb != xa) ? 1 : 0) | ((yb != ya) ? 2 : 0);
-              // a clamped (out-of-range) tap has zero weight (make_taps): aliasing it onto its in-range neighbour's
-              // address is harmless, the four reads are always in bounds.
-              q.w00 = tp.w00; q.w01 = tp.w01; q.w10 = tp.w10; q.w11 = tp.w11;
-              lo_y = min(lo_y, ya); hi_y = max(hi_y, yb); lo_x = min(lo_x, xa); hi_x = max(hi_x, xb);
-            }
-          }
-        }
-        sp[k] = q;
-      }
-      if (pt == 0) { red[0] = 1 << 30; red[1] = -1; red[2] = 1 << 30; red[3] = -1; }
-      samp_sync();
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
-        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
-      }
-      if (lane == 0) { atomicMin(&red[0], lo_y); atomicMax(&red[1], hi_y); atomicMin(&red[2], lo_x); atomicMax(&red[3], hi_x); }
-      samp_sync();
-      const int ymin = red[0], ymax = red[1], xmin = red[2], xmax = red[3];
-      const bool any_live = ymax >= ymin;
-      const int oy = any_live ? ymin : 0, ox = any_live ? (xmin & ~3) : 0;  // TMA traps on an inner coordinate that is not 16-byte aligned (measured)
-      const int foot = (!any_live || ((ymax - oy) < FP_H && (xmax - ox) < FP_W)) ? 1 : 0;
-#pragma unroll
-      for (int k = 0; k < T_KPOS; ++k)
-        if (sp[k].off >= 0) sp[k].off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * W + xa_[k];
-      samp_sync();  // red[] is re-initialised by the next setup
-      if (pt == 0) {
-        int* mt = meta + 4 * slot;
-        mt[0] = oy; mt[1] = ox; mt[2] = foot;
-        mbar_arrive(metafull(slot));  // release: the issuer's wait acquires the three words
-      }
-      foot_out = foot;
-    };
-
-    SampPos cur[T_KPOS], nxt[T_KPOS];
-    int foot = 0, foot_n = 0, gchunk = 0, it = 0;
-    if ((int)blockIdx.x < ntiles) setup(blockIdx.x, 0, cur, foot);
+    int gchunk = 0, it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = tile / (tiles_x * tiles_y);
       int b2 = b + shift;
       if (b2 >= B) b2 -= B;
       const float* f2b = f2 + (size_t)b2 * f2_bs;
-      const int ntile = tile + (int)gridDim.x;
-      if (ntile < ntiles) setup(ntile, (it + 1) & 1, nxt, foot_n);
+      // this tile's taps, from the table the compute warps filled one tile ago
+      const int slot = it & 1;
+      mbar_wait(tabfull(slot), (uint32_t)((it >> 1) & 1));
+      const int foot = reinterpret_cast<const volatile int*>(meta)[4 * slot + 2];
+      float4 wq[T_KPOS];
+      int od[T_KPOS];
+      {
+        const float4* tw = reinterpret_cast<const float4*>(tab + slot * T_TAB_WORDS);
+        const int* to = reinterpret_cast<const int*>(tab + slot * T_TAB_WORDS + NHALO * 4);
+#pragma unroll
+        for (int k = 0; k < T_KPOS; ++k) {
+          const int h = pt + k * T_NSAMP;
+          wq[k] = h < NHALO ? tw[h] : make_float4(0.f, 0.f, 0.f, 0.f);
+          od[k] = h < NHALO ? to[h] : -1;
+        }
+      }
       for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
         const int s = gchunk % NS, fs = gchunk % T_NFS;
         mbar_wait(fpfull(fs), (uint32_t)((gchunk / T_NFS) & 1));
@@ -613,18 +672,27 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
             if (h < NHALO) {
               const int hr = h / F2_WV, hx = h - hr * F2_WV;
               float* dst = st + hr * F2_P + hx;
-              const bool live = cur[k].off >= 0;
-              const float* pq = fp + (live ? cur[k].off : 0);
-              const int dx = cur[k].dxy & 1, dy = (cur[k].dxy & 2) ? FP_W : 0;
+              const bool live = od[k] >= 0;
+              const float* pq = fp + (live ? (od[k] >> 2) : 0);
+              const int dx = od[k] & 1, dy = (od[k] & 2) ? FP_W : 0;  // dead: od = -1 -> dx = 1, dy = FP_W, still inside
+              // all 32 tap loads of the position first, then the arithmetic, then the stores: a shared-memory store between
+              // the channels would serialise them (the compiler cannot prove dst and the footprint do not alias)
+              float t[4][CC];
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
                 const float* pc = pq + cc * (FP_H * FP_W);
-                float a = __fmul_rn(pc[0], cur[k].w00);  // tap order of grid_sampler_2d
-                a = fmaf(pc[dx], cur[k].w01, a);
-                a = fmaf(pc[dy], cur[k].w10, a);
-                a = fmaf(pc[dy + dx], cur[k].w11, a);
-                dst[cc * (F2_H * F2_P)] = live ? a : 0.f;
+                t[0][cc] = pc[0]; t[1][cc] = pc[dx]; t[2][cc] = pc[dy]; t[3][cc] = pc[dy + dx];
               }
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) {
+                float a = __fmul_rn(t[0][cc], wq[k].x);  // tap order of grid_sampler_2d
+                a = fmaf(t[1][cc], wq[k].y, a);
+                a = fmaf(t[2][cc], wq[k].z, a);
+                a = fmaf(t[3][cc], wq[k].w, a);
+                t[0][cc] = live ? a : 0.f;
+              }
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) dst[cc * (F2_H * F2_P)] = t[0][cc];
             }
           }
         } else {  // divergent flow: gather the taps from global memory
@@ -634,9 +702,9 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
             if (h < NHALO) {
               const int hr = h / F2_WV, hx = h - hr * F2_WV;
               float* dst = st + hr * F2_P + hx;
-              const bool live = cur[k].off >= 0;
-              const float* pq = f2b + (size_t)c0 * HW + (live ? cur[k].off : 0);
-              const int dx = cur[k].dxy & 1, dy = (cur[k].dxy & 2) ? W : 0;
+              const bool live = od[k] >= 0;
+              const float* pq = f2b + (size_t)c0 * HW + (live ? (od[k] >> 2) : 0);
+              const int dx = live ? (od[k] & 1) : 0, dy = (live && (od[k] & 2)) ? W : 0;
               float t[4][CC];
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
@@ -649,10 +717,10 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
               }
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
-                float a = __fmul_rn(t[0][cc], cur[k].w00);
-                a = fmaf(t[1][cc], cur[k].w01, a);
-                a = fmaf(t[2][cc], cur[k].w10, a);
-                dst[cc * (F2_H * F2_P)] = fmaf(t[3][cc], cur[k].w11, a);
+                float a = __fmul_rn(t[0][cc], wq[k].x);
+                a = fmaf(t[1][cc], wq[k].y, a);
+                a = fmaf(t[2][cc], wq[k].z, a);
+                dst[cc * (F2_H * F2_P)] = fmaf(t[3][cc], wq[k].w, a);
               }
             }
           }
@@ -663,9 +731,6 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
           mbar_arrive(fpempty(fs));
         }
       }
-#pragma unroll
-      for (int k = 0; k < T_KPOS; ++k) cur[k] = nxt[k];
-      foot = foot_n;
     }
   }
 }
