@@ -66,6 +66,20 @@ struct ProdPos {  // one halo (or f1) position owned by a producer thread
 
 // ---------------------------------------------------------------------------------------------------------
 // COMPUTE role (warps 0-8 of either kernel): consumes the NS-slot ring of [f1 tile | f2 halo tile] chunks.
+// Role cycle counters (block 0, one thread per role), filled when the launch is made with IRR_CORR_CTR=1 and read back
+// with irrdbg_corr_counters(): [0] compute wait-full [1] set-up [2] epilogue [3] total | [8] issuer wait-table
+// [9] wait-empty [10] wait-fpempty [11] total | [16] sampler wait-table [17] wait-fpfull [18] wait-empty [19] total.
+__device__ unsigned long long corr_ctr[32];
+__device__ __forceinline__ void mbar_wait_ctr(uint32_t bar, uint32_t parity, bool on, int idx) {
+  if (on) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    corr_ctr[idx] += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
 struct NoTileHook {
   __device__ __forceinline__ void setup(int, int) const {}
 };
@@ -75,10 +89,12 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
                                              const float* __restrict__ f1, long long f1_bs,
                                              const float* __restrict__ f2, long long f2_bs, float* __restrict__ out,
                                              long long out_bs, int B, int C, int H, int W, int shift, float slope,
-                                             int vec_ok, int tiles_x, int tiles_y, int ntiles) {
+                                             int vec_ok, int tiles_x, int tiles_y, int ntiles, int ctr = 0) {
   const int tid = threadIdx.x;
   const int HW = H * W;
   const int nchunks = (C + CC - 1) / CC;
+  const bool con = ctr && blockIdx.x == 0 && tid == 0;
+  const long long ct0 = con ? clock64() : 0;
   // Thread -> (tile row r, displacement row dyi, 8-pixel strip s8).  The 72 (r, dyi) pairs are dealt to the 9 warps
   // sorted by the f2 halo row they read (h = r + dyi), 8 pairs x 4 strips per warp: a warp then touches only 2-4
   // distinct f2 rows and ~5 f1 rows, and lanes that share a row and strip read the SAME 16 bytes — one shared-memory
@@ -106,7 +122,11 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     const int ty = (tile / tiles_x) % tiles_y;
     const int b = tile / (tiles_x * tiles_y);
     const int y0 = ty * TH, x0 = tx * TW;
-    if (tile + (int)gridDim.x < ntiles) hook.setup(tile + (int)gridDim.x, it + 1);  // accumulators are dead here
+    {
+      const long long t0 = con ? clock64() : 0;
+      if (tile + (int)gridDim.x < ntiles) hook.setup(tile + (int)gridDim.x, it + 1);  // accumulators are dead here
+      if (con) corr_ctr[1] += (unsigned long long)(clock64() - t0);
+    }
     float acc[ND][PX];
 #pragma unroll
     for (int d = 0; d < ND; ++d)
@@ -143,7 +163,7 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
       const int s = gchunk % NS;
       const uint32_t ph = (uint32_t)((gchunk / NS) & 1);
-      mbar_wait(full0 + 8u * s, ph);
+      mbar_wait_ctr(full0 + 8u * s, ph, con, 0);
       const float* f1s = smem + s * STAGE_ELEMS;
       const float* f2s = f1s + F1_ELEMS;
 #pragma unroll 2
@@ -168,18 +188,38 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     }
 
     // ---- epilogue: mean over channels (pwc_modules.py:59 / .cu:107 divide by nelems), LeakyReLU (IRR_PWC.py:94-95)
+    const long long te0 = con ? clock64() : 0;
     const int gy = y0 + r;
     const int gx = x0 + s8 * PX;
     if (gy < H && gx < W) {
       const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
       float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
-      // scale in place first, then issue the 18 stores back to back (a temporary per displacement makes every store
-      // wait for the previous one to release its registers)
+      // scale in place first, then issue the stores back to back (a temporary per displacement makes every store
+      // wait for the previous one to release its registers).  slope in [0, 1]: leaky(v) == max(v, v * slope).
+      if (slope >= 0.f && slope <= 1.f) {
 #pragma unroll
-      for (int d = 0; d < ND; ++d)
+        for (int d = 0; d < ND; ++d)
 #pragma unroll
-        for (int p = 0; p < PX; ++p) acc[d][p] = leaky(acc[d][p] * inv_c, slope);
-      if (vec_ok && gx + PX <= W) {
+          for (int p = 0; p < PX; ++p) {
+            const float v = acc[d][p] * inv_c;
+            acc[d][p] = fmaxf(v, v * slope);
+          }
+      } else {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+#pragma unroll
+          for (int p = 0; p < PX; ++p) acc[d][p] = leaky(acc[d][p] * inv_c, slope);
+      }
+      if (vec_ok == 2 && gx + PX <= W) {
+        // 32-byte stores (sm_100 st.global.v8.f32): one full sector per lane per instruction, 9 stores per thread
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op + (size_t)d * HW), "f"(acc[d][0]),
+                       "f"(acc[d][1]), "f"(acc[d][2]), "f"(acc[d][3]), "f"(acc[d][4]), "f"(acc[d][5]), "f"(acc[d][6]),
+                       "f"(acc[d][7])
+                       : "memory");
+        }
+      } else if (vec_ok && gx + PX <= W) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
           float4* q = reinterpret_cast<float4*>(op + (size_t)d * HW);
@@ -194,7 +234,9 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
             if (gx + p < W) op[(size_t)d * HW + p] = acc[d][p];
       }
     }
+    if (con) corr_ctr[2] += (unsigned long long)(clock64() - te0);
   }
+  if (con) corr_ctr[3] += (unsigned long long)(clock64() - ct0);
 }
 
 template <bool FUSED>
@@ -444,7 +486,10 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
 // sampler warps it was 48 % of their time and the compute warps waited 43 % of theirs).
 constexpr int T_NS_PLAIN = 6, T_NS_FUSED = 3, T_NFS = 2;
 constexpr int T_PLAIN_THREADS = NCOMP + 32;   // plain: 9 compute warps + the issuer's warp (no register cap at 128)
-constexpr int T_NSAMP = 192;                  // sampler threads (warps 10-15)
+constexpr int T_NSAMP = 192;                  // sampler threads (warps 9-11, 13-15)
+// Warp w issues on scheduler w % 4: compute warps 0-8 load the schedulers 3:2:2:2, so the six sampler warps go to
+// schedulers 1-3 and the (single-thread) copy issuer's warp is the one that shares scheduler 0.
+constexpr int T_ISSUER_FUSED = 12 * 32;
 constexpr int T_KPOS = (NHALO + T_NSAMP - 1) / T_NSAMP;  // 4 halo positions per sampler thread
 constexpr int T_KSET = (NHALO + NCOMP - 1) / NCOMP;      // 3 halo positions per compute thread in the set-up
 constexpr uint32_t T_F1_BYTES = F1_ELEMS * 4, T_F2_BYTES = F2_ELEMS * 4, T_FP_BYTES = FP_ELEMS * 4;
@@ -549,7 +594,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
                     const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                     const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
                     GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
-                    int ntiles) {
+                    int ntiles, int ctr) {
   constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
   extern __shared__ __align__(1024) float smem[];
   float* fpr = smem + NS * STAGE_ELEMS;                          // footprint ring (FUSED)
@@ -589,14 +634,16 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.tiles_x = tiles_x;
       hook.tiles_y = tiles_y; hook.tab = tab; hook.meta = meta; hook.red = red; hook.tabfull0 = tabfull(0);
       corr_compute<NS, false>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
-                              vec_ok, tiles_x, tiles_y, ntiles);
+                              vec_ok, tiles_x, tiles_y, ntiles, ctr);
     } else {
       corr_compute<NS, false>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift,
-                              slope, vec_ok, tiles_x, tiles_y, ntiles);
+                              slope, vec_ok, tiles_x, tiles_y, ntiles, ctr);
     }
-  } else if (tid == NCOMP) {
+  } else if (tid == (FUSED ? T_ISSUER_FUSED : NCOMP)) {
     // ============================== COPY ISSUER (one thread) ==============================
     int gchunk = 0, it = 0;
+    const bool con = ctr && blockIdx.x == 0;
+    const long long ct0 = con ? clock64() : 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
@@ -606,13 +653,13 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       if (b2 >= B) b2 -= B;
       int oy = 0, ox = 0, foot = 0;
       if (FUSED) {
-        mbar_wait(tabfull(it & 1), (uint32_t)((it >> 1) & 1));
+        mbar_wait_ctr(tabfull(it & 1), (uint32_t)((it >> 1) & 1), con, 8);
         const volatile int* mt = meta + 4 * (it & 1);
         oy = mt[0]; ox = mt[1]; foot = mt[2];
       }
       for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
         const int s = gchunk % NS;
-        mbar_wait(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1));
+        mbar_wait_ctr(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1), con, 9);
         const uint32_t st = smem_u32(smem + s * STAGE_ELEMS);
         if (!FUSED) {
           mbar_expect_tx(full(s), T_F1_BYTES + T_F2_BYTES);
@@ -622,7 +669,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
           mbar_expect_tx(full(s), T_F1_BYTES);
           tma_load_4d(st, &m1, x0, y0, ci * CC, b, full(s));
           const int fs = gchunk % T_NFS;
-          mbar_wait(fpempty(fs), (uint32_t)(((gchunk / T_NFS) & 1) ^ 1));
+          mbar_wait_ctr(fpempty(fs), (uint32_t)(((gchunk / T_NFS) & 1) ^ 1), con, 10);
           if (foot) {
             mbar_expect_tx(fpfull(fs), T_FP_BYTES);
             tma_load_4d(smem_u32(fpr + fs * FP_ELEMS), &m2, ox, oy, ci * CC, b2, fpfull(fs));
@@ -632,11 +679,14 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         }
       }
     }
-  } else if (FUSED && tid >= CORR_THREADS - T_NSAMP) {
-    // ============================== SAMPLERS (warps 10-15) ==============================
-    const int pt = tid - (CORR_THREADS - T_NSAMP);
+    if (con) corr_ctr[11] += (unsigned long long)(clock64() - ct0);
+  } else if (FUSED && tid >= NCOMP && (tid >> 5) != (T_ISSUER_FUSED >> 5)) {
+    // ============================== SAMPLERS (warps 9-11, 13-15) ==============================
+    const int pt = tid - NCOMP - ((tid >> 5) > (T_ISSUER_FUSED >> 5) ? 32 : 0);
     const int lane = tid & 31;
     int gchunk = 0, it = 0;
+    const bool con = ctr && blockIdx.x == 0 && pt == 0;
+    const long long ct0 = con ? clock64() : 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = tile / (tiles_x * tiles_y);
       int b2 = b + shift;
@@ -644,7 +694,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       const float* f2b = f2 + (size_t)b2 * f2_bs;
       // this tile's taps, from the table the compute warps filled one tile ago
       const int slot = it & 1;
-      mbar_wait(tabfull(slot), (uint32_t)((it >> 1) & 1));
+      mbar_wait_ctr(tabfull(slot), (uint32_t)((it >> 1) & 1), con, 16);
       const int foot = reinterpret_cast<const volatile int*>(meta)[4 * slot + 2];
       float4 wq[T_KPOS];
       int od[T_KPOS];
@@ -660,8 +710,8 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       }
       for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
         const int s = gchunk % NS, fs = gchunk % T_NFS;
-        mbar_wait(fpfull(fs), (uint32_t)((gchunk / T_NFS) & 1));
-        mbar_wait(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1));
+        mbar_wait_ctr(fpfull(fs), (uint32_t)((gchunk / T_NFS) & 1), con, 17);
+        mbar_wait_ctr(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1), con, 18);
         float* st = smem + s * STAGE_ELEMS + F1_ELEMS;
         const int c0 = ci * CC;
         if (foot) {
@@ -732,6 +782,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         }
       }
     }
+    if (con) corr_ctr[19] += (unsigned long long)(clock64() - ct0);
   }
 }
 
@@ -771,6 +822,11 @@ static bool corr_no_tma() {  // IRR_CORR_NO_TMA=1: force the cp.async kernel (A/
   return e && e[0] == '1';
 }
 
+static bool corr_ctr_on() {  // IRR_CORR_CTR=1: role cycle counters (debug)
+  const char* e = getenv("IRR_CORR_CTR");
+  return e && e[0] == '1';
+}
+
 template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
@@ -786,6 +842,8 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
     attr_done = true;
   }
   int vec_ok = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec_ok && (W % 8 == 0) && (((long long)H * W) % 8 == 0) && (out_bs % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0))
+    vec_ok = 2;  // every 8-pixel strip of every output plane is 32-byte aligned
   // 16-byte cp.async staging needs 16-byte aligned rows in both operands
   int vec_in = (W % 4 == 0) && (f1_bs % 4 == 0) && (f2_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(f2) & 15) == 0);
@@ -808,8 +866,14 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
         }
         tattr_done = true;
       }
-      corr_tma_kernel<FUSED><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g,
-                                                                B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles);
+      const int ctr = corr_ctr_on() ? 1 : 0;
+      if (ctr) {
+        static const unsigned long long zeros[32] = {0};
+        cudaMemcpyToSymbolAsync(corr_ctr, zeros, sizeof(zeros), 0, cudaMemcpyHostToDevice, st);
+      }
+      corr_tma_kernel<FUSED><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(
+          m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,
+          ntiles, ctr);
       return check_launch(fn);
     }
   }
@@ -849,6 +913,17 @@ int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, 
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
   return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift,
                            leaky_slope, as_stream(stream));
+}
+
+// Debug hook (not part of the ABI in include/irr_b200.h), scripts/corr_counters.py
+int irrdbg_corr_counters(unsigned long long* out32) {
+  if (!out32) return fail_arg("irrdbg_corr_counters", "null pointer");
+  cudaError_t e = cudaMemcpyFromSymbol(out32, corr_ctr, 32 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    set_error("irrdbg_corr_counters: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
 }
 
 int irr_correlation_generic_out_shape(int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,
