@@ -143,6 +143,11 @@ int irr_resize_bilinear_ac_fwd(const float* x, long long x_bs, float* y, long lo
 int irr_scale_channels_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
                            float scale_even, float scale_odd, irr_stream_t stream);
 
+/* BASELINE config 5 (mixed bf16 features; no reference counterpart — the reference is fp32 only):
+ * y = float(bfloat16(x)), round-to-nearest-even, on a channel-slice view.  In place (y == x) is allowed. */
+int irr_round_bf16_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
+                       irr_stream_t stream);
+
 /* A10 — upsample_factor2 (models/irr_modules.py:21-27): nearest x2, then (only if (OH,OW) != (2H,2W)) bilinear
  * align_corners=False resize to OH x OW. */
 int irr_upsample_nearest2x_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
@@ -160,6 +165,15 @@ int irr_channel_l2norm_fwd(const float* x, long long x_bs, float* y, long long y
  * channel of src (models/irr_modules.py:89-104, 130-138).  logits: B x 9 x H x W, src/out: B x C x H x W. */
 int irr_refine_gather_fwd(const float* logits, long long logits_bs, const float* src, long long src_bs, float* out,
                           long long out_bs, int B, int C, int H, int W, irr_stream_t stream);
+
+/* §8(f).1 — evaluation metrics of the reference's eval-mode losses (losses.py:8-10, 24-37, 634-636, 688-697), one
+ * launch per batch, deterministic.  flow / target: B x 2 x H x W; valid, occ_logits, target_occ: B x 1 x H x W or NULL.
+ * sums: B x 8 float64 = { S epe*valid, S valid, S outlier, S pred*true, S pred, S true, 0, 0 } with
+ * epe = ||target - flow||, outlier = (epe*valid > 3) & (epe*valid / (||target|| + 1e-8) > 0.05), pred = round(sigmoid(occ)). */
+int irr_eval_metrics_fwd(const float* flow, long long flow_bs, const float* target, long long target_bs,
+                         const float* valid, long long valid_bs, const float* occ_logits, long long occ_bs,
+                         const float* target_occ, long long tocc_bs, double* sums, int B, int H, int W,
+                         irr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -81,7 +81,16 @@ class PWCNet(nn.Module):
         self.refine_occ = RefineOcc(1 + 32 + 32)
         self.corr_params = {"pad_size": self.search_range, "kernel_size": 1, "max_disp": self.search_range,
                             "stride1": 1, "stride2": 1, "corr_multiply": 1}
+        # BASELINE config 5 ("mixed bf16 features"): "bf16" rounds the feature pyramid to bf16 values before the warp /
+        # correlation / 1x1 convs (a capability the fp32-only reference does not have; default = the reference's fp32)
+        self.feature_dtype = "fp32"
         initialize_msra(self.modules())
+
+    def set_feature_dtype(self, dtype: str):
+        if dtype not in ("fp32", "bf16"):
+            raise ValueError("feature_dtype must be 'fp32' or 'bf16'")
+        self.feature_dtype = dtype
+        return self
 
     # ------------------------------------------------------------------------------------------------ stages
     def estimator_level(self, l, feat, flow_up, occ_up, imgs, height_im, width_im, record=None):
@@ -198,7 +207,11 @@ class PWCNet(nn.Module):
         B, _, height_im, width_im = x1_raw.shape
         with torch.no_grad():
             imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()  # (2B, 3, H, W)
-            pyramid = self.feature_pyramid_extractor(imgs) + [imgs]
+            pyramid = self.feature_pyramid_extractor(imgs)
+            if self.feature_dtype == "bf16":
+                for f in pyramid:
+                    ops.round_bf16(f, out=f)
+            pyramid = pyramid + [imgs]
             flow = occ = None
             for l, feat in enumerate(pyramid):
                 _, _, h, w = feat.shape

@@ -42,9 +42,11 @@ PROTOTYPES = {
                             c_f, c_i, c_fp, c_ll, c_fp, c_ll, c_f, c_f, c_i, c_fp, C.c_size_t, c_fp],
     "irr_resize_bilinear_ac_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_fp],
     "irr_scale_channels_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_f, c_f, c_fp],
+    "irr_round_bf16_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],
     "irr_upsample_nearest2x_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_sub_spatial_mean_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
     "irr_channel_l2norm_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],
+    "irr_eval_metrics_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_fp],
     "irr_refine_gather_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
 }
 _RESTYPES = {"irr_last_error": C.c_char_p, "irr_conv2d_packed_bytes": C.c_size_t,

@@ -50,6 +50,21 @@ __global__ void scale_channels_kernel(const float* __restrict__ x, long long x_b
   y[(size_t)b * y_bs + (size_t)c * HW + pix] = __fmul_rn(v, (c & 1) ? s_odd : s_even);
 }
 
+// BASELINE config 5 ("mixed bf16 features"): y = float(bf16_rn(x)) — the feature pyramid carries bf16 VALUES (what a
+// `.bfloat16()` cast before the warp / correlation produces) in the fp32 NCHW layout every consumer already reads.
+__global__ void round_bf16_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ y, long long y_bs,
+                                  long long CHW, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long e = i % CHW;
+  long long b = i / CHW;
+  float v = __ldg(x + (size_t)b * x_bs + e);
+  uint32_t u = __float_as_uint(v);
+  // round to nearest even on the upper 16 bits (NaN stays NaN: the quiet bit is forced, as torch's cast does)
+  uint32_t r = ((u & 0x7fffffffu) > 0x7f800000u) ? ((u >> 16) | 0x0040u) : ((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+  y[(size_t)b * y_bs + e] = __uint_as_float(r << 16);
+}
+
 // upsample_factor2 (models/irr_modules.py:21-27).
 __global__ void upsample_nearest2x_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ y,
                                           long long y_bs, int C, int H, int W, int OH, int OW, int exact,
@@ -109,6 +124,60 @@ __global__ void __launch_bounds__(512) sub_spatial_mean_kernel(const float* __re
   __syncthreads();
   float m = mean_s;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) q[i] = __ldg(p + i) - m;
+}
+
+// Evaluation metrics of the reference's eval-mode losses, one CTA per image, deterministic:
+//   sums[b] = { S epe*valid, S valid, S outlier, S pred*true, S pred, S true, 0, 0 }   (float64)
+// epe = ||target - flow||_2 per pixel (losses.py:8-10); valid == nullptr -> all ones (losses.py:635);
+// outlier = (epe*valid > 3) * (epe*valid / (||target||_2 + 1e-8) > 0.05) * valid (losses.py:693-697);
+// pred = round(sigmoid(occ logits)) (losses.py:636), true = target_occ; F1 is finished on the host (losses.py:27-37).
+__global__ void __launch_bounds__(1024) eval_metrics_kernel(const float* __restrict__ flow, long long flow_bs,
+                                                            const float* __restrict__ target, long long target_bs,
+                                                            const float* __restrict__ valid, long long valid_bs,
+                                                            const float* __restrict__ occ, long long occ_bs,
+                                                            const float* __restrict__ tocc, long long tocc_bs,
+                                                            double* __restrict__ sums, int HW) {
+  const int b = blockIdx.x;
+  const float* fu = flow + (size_t)b * flow_bs;
+  const float* tu = target + (size_t)b * target_bs;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float t0 = __ldg(tu + i), t1 = __ldg(tu + HW + i);
+    const float d0 = __fsub_rn(t0, __ldg(fu + i)), d1 = __fsub_rn(t1, __ldg(fu + HW + i));
+    const float epe = sqrtf(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
+    const float v = valid ? __ldg(valid + (size_t)b * valid_bs + i) : 1.0f;
+    const float ev = __fmul_rn(epe, v);
+    const float mag = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1))), 1e-8f);
+    acc[0] += (double)ev;
+    acc[1] += (double)v;
+    acc[2] += (double)(((ev > 3.0f) && (__fdiv_rn(ev, mag) > 0.05f)) ? v : 0.0f);
+    if (occ) {
+      const float x = __ldg(occ + (size_t)b * occ_bs + i);
+      const float sgm = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+      const float pr = sgm > 0.5f ? 1.0f : 0.0f;  // torch.round is half-to-even: 0.5 -> 0
+      const float tr = tocc ? __ldg(tocc + (size_t)b * tocc_bs + i) : 0.0f;
+      acc[3] += (double)(pr * tr);
+      acc[4] += (double)pr;
+      acc[5] += (double)tr;
+    }
+  }
+  __shared__ double red[6][32];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double t = acc[k];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double t = (threadIdx.x < (blockDim.x >> 5)) ? red[k][threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) sums[(size_t)b * 8 + k] = t;
+    }
+    if (threadIdx.x == 0) { sums[(size_t)b * 8 + 6] = 0.0; sums[(size_t)b * 8 + 7] = 0.0; }
+  }
 }
 
 __global__ void channel_l2norm_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ y,
@@ -196,6 +265,16 @@ int irr_scale_channels_fwd(const float* x, long long x_bs, float* y, long long y
   return check_launch(fn);
 }
 
+int irr_round_bf16_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
+                       irr_stream_t stream) {
+  const char* fn = "irr_round_bf16_fwd";
+  IRR_REQUIRE(x && y, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && C > 0 && HW > 0, fn, "non-positive size");
+  long long total = (long long)B * C * HW;
+  round_bf16_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(x, x_bs, y, y_bs, (long long)C * HW, total);
+  return check_launch(fn);
+}
+
 int irr_upsample_nearest2x_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
                                int OH, int OW, irr_stream_t stream) {
   const char* fn = "irr_upsample_nearest2x_fwd";
@@ -225,6 +304,19 @@ int irr_channel_l2norm_fwd(const float* x, long long x_bs, float* y, long long y
   IRR_REQUIRE(B > 0 && C > 0 && HW > 0, fn, "non-positive size");
   long long total = (long long)B * HW;
   channel_l2norm_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(x, x_bs, y, y_bs, C, HW, total);
+  return check_launch(fn);
+}
+
+int irr_eval_metrics_fwd(const float* flow, long long flow_bs, const float* target, long long target_bs,
+                         const float* valid, long long valid_bs, const float* occ_logits, long long occ_bs,
+                         const float* target_occ, long long tocc_bs, double* sums, int B, int H, int W,
+                         irr_stream_t stream) {
+  const char* fn = "irr_eval_metrics_fwd";
+  IRR_REQUIRE(flow && target && sums, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < 0x7fffffffLL, fn, "bad size");
+  IRR_REQUIRE(!(target_occ && !occ_logits), fn, "target_occ without occ_logits");
+  eval_metrics_kernel<<<B, 1024, 0, as_stream(stream)>>>(flow, flow_bs, target, target_bs, valid, valid_bs, occ_logits,
+                                                         occ_bs, target_occ, tocc_bs, sums, H * W);
   return check_launch(fn);
 }
 

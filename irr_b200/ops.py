@@ -244,6 +244,16 @@ def scale_channels(x, out=None, s_even: float = 1.0, s_odd: float = 1.0):
     return out
 
 
+def round_bf16(x, out=None):
+    """y = x.bfloat16().float() (BASELINE config 5: bf16-valued features in the fp32 layout); ``out=x`` rounds in place."""
+    B, C, H, W = x.shape
+    if out is None:
+        out = _new(x, C, H, W)
+    px, sx = _v(x, "x"); po, so = _v(out, "out")
+    _launch("round_bf16", None, _lib.load().irr_round_bf16_fwd, px, sx, po, so, B, C, H * W, _stream())
+    return out
+
+
 def upsample_nearest2x(x, OH: int, OW: int, out=None):
     B, C, H, W = x.shape
     if out is None:
@@ -279,3 +289,18 @@ def refine_gather(logits, src, out=None):
     pl, sl = _v(logits, "logits"); ps, ss = _v(src, "src"); po, so = _v(out, "out")
     _launch("refine_gather", None, _lib.load().irr_refine_gather_fwd, pl, sl, ps, ss, po, so, B, C, H, W, _stream())
     return out
+
+
+def eval_metrics(flow, target, valid=None, occ_logits=None, target_occ=None):
+    """Per-image sums for the reference's eval-mode losses (include/irr_b200.h irr_eval_metrics_fwd): float64 (B, 8)
+    tensor { S epe*valid, S valid, S outlier, S pred*true, S pred, S true, 0, 0 }."""
+    B, C, H, W = flow.shape
+    assert C == 2 and tuple(target.shape) == (B, 2, H, W)
+    pf, sf = _v(flow, "flow"); pt, st = _v(target, "target")
+    pv, sv = _v(valid, "valid") if valid is not None else (None, 0)
+    po, so = _v(occ_logits, "occ_logits") if occ_logits is not None else (None, 0)
+    pq, sq = _v(target_occ, "target_occ") if target_occ is not None else (None, 0)
+    sums = torch.empty((B, 8), dtype=torch.float64, device=flow.device)
+    _launch("eval_metrics", None, _lib.load().irr_eval_metrics_fwd, pf, sf, pt, st, pv, sv, po, so, pq, sq,
+            sums.data_ptr(), B, H, W, _stream())
+    return sums

@@ -131,11 +131,35 @@ def gen_modules():
     print("modules.npz", len(cases))
 
 
+def gen_losses():
+    """Eval-branch outputs of the reference's losses.py on oracle/losses_oracle.synthetic_eval_case inputs."""
+    import losses as ref_losses
+    from oracle import losses_oracle as LO
+
+    class Args:
+        batch_size = 3
+        model_div_flow = 0.05
+    cases = {}
+    for seed in (0, 1, 2):
+        out, tgt = LO.synthetic_eval_case(seed)
+        with torch.no_grad():
+            a = ref_losses.MultiScaleEPE_PWC_Bi_Occ_upsample(Args()).eval()(dict(out), dict(tgt))
+            b = ref_losses.MultiScaleEPE_PWC_Bi_Occ_upsample_KITTI(Args()).eval()(dict(out), dict(tgt))
+        cases[f"sintel_{seed}"] = np.array([a["epe"].item(), a["F1"].item()], np.float64)
+        cases[f"kitti_{seed}"] = np.array([b["epe"].item(), b["outlier"].item()], np.float64)
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **cases)
+    print("losses.npz", {k: v.tolist() for k, v in cases.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        gen_losses()
+        sys.exit(0)
     gen_cost_volume()
     gen_warp()
     gen_modules()
     gen_models()
+    gen_losses()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -175,7 +175,7 @@ def occ_upsample(p: Params, occ, x, prefix="occ_shuffle_upsample"):
 
 
 # --------------------------------------------------------------------------- models
-def irr_pwc_forward(p: Params, img1, img2, div_flow=0.05, record: Optional[dict] = None):
+def irr_pwc_forward(p: Params, img1, img2, div_flow=0.05, record: Optional[dict] = None, feature_bf16: bool = False):
     """Eval-mode ``IRR_PWC.PWCNet.forward`` (models/IRR_PWC.py:51-184), as executed.
 
     Note F6: models/IRR_PWC.py:128-129 call rescale_flow on ``flow_cont_*``
@@ -184,8 +184,13 @@ def irr_pwc_forward(p: Params, img1, img2, div_flow=0.05, record: Optional[dict]
     ``record`` (optional dict) receives every stage tensor for teacher-forced tests.
     """
     B, _, Him, Wim = img1.shape
-    pyr1 = feature_pyramid(p, img1) + [img1]
-    pyr2 = feature_pyramid(p, img2) + [img2]
+    pyr1 = feature_pyramid(p, img1)
+    pyr2 = feature_pyramid(p, img2)
+    if feature_bf16:  # BASELINE config 5: the feature pyramid is cast to bf16 before the warp / correlation (not in the
+        # reference, which is fp32 only): bf16 values carried in fp32 tensors, everything downstream unchanged
+        pyr1 = [f.bfloat16().float() for f in pyr1]
+        pyr2 = [f.bfloat16().float() for f in pyr2]
+    pyr1, pyr2 = pyr1 + [img1], pyr2 + [img2]
     h0, w0 = pyr1[0].shape[2:]
     z = lambda c: torch.zeros(B, c, h0, w0, dtype=img1.dtype, device=img1.device)
     flow_f, flow_b, occ_f, occ_b = z(2), z(2), z(1), z(1)

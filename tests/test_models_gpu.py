@@ -146,6 +146,29 @@ def test_irr_end_to_end_vs_oracle_and_golden(irr_case, cuda, golden_dir):
     assert d["flow"] <= 1.0                   # chaotic tail bound (reference fp32-vs-fp64 is 0.16-1.6 px)
 
 
+@pytest.mark.parametrize("feat", ["fp32", "bf16"])
+def test_irr_kitti_shape_end_to_end(cuda, conv_math, feat):
+    """BASELINE config 5's shape (375 x 1242: level widths 621/311/156/78/39/20 — only two of them 16-byte aligned, so the
+    cp.async correlation kernel, the gather conv variant and every ragged tail run), fp32 and with the feature pyramid
+    rounded to bf16 ("mixed bf16 features").  The oracle gets the same rounding; tolerance as for config 3 — the bf16
+    cast happens once, identically on both sides, it does not loosen the comparison."""
+    if conv_math != "3xf16":
+        pytest.skip("KITTI-shape run only in the default conv math")
+    m, p = build("IRR_PWC", cuda)
+    m.set_feature_dtype(feat)
+    i1, i2, gt = O.synthetic_pair(1, 375, 1242, seed=5, max_flow=10.0)
+    with torch.no_grad():
+        ref = O.irr_pwc_forward(p, i1, i2, feature_bf16=(feat == "bf16"))
+        got = m({"input1": i1.to(cuda), "input2": i2.to(cuda)})
+    assert got["flow"].shape == (1, 2, 375, 1242) and got["occ"].shape == (1, 1, 375, 1242)
+    d, e = _report(f"IRR_PWC 375x1242 features={feat} vs oracle(CPU)", got, ref, gt)
+    assert e <= 2e-2 and d["flow"] <= 1.0
+    if feat == "bf16":  # and the switch really changes the result
+        with torch.no_grad():
+            ref32 = O.irr_pwc_forward(p, i1, i2)
+        assert O.epe(ref32["flow"], ref["flow"]).item() > 1e-4
+
+
 @pytest.mark.parametrize("name,hw", [("PWCNet", (128, 128)), ("PWCNet_irr_occ_bi", (128, 192))])
 def test_other_models_end_to_end(cuda, golden_dir, name, hw):
     H, W = hw

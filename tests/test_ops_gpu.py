@@ -234,6 +234,23 @@ def test_resize_scale_nearest(cuda, golden_dir):
         assert (got - ref).abs().max().item() <= 5e-6  # CPU vs CUDA-order bilinear (align_corners=False) differ by ulps
 
 
+def test_round_bf16(cuda):
+    """irr_round_bf16_fwd == x.bfloat16().float() bit for bit (RNE, ties, subnormals, inf, NaN), slices, in place."""
+    from irr_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 5, 7, 9, generator=g) * torch.logspace(-42, 30, 2 * 5 * 7 * 9).view(2, 5, 7, 9)
+    x.view(-1)[:8] = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), 1.00390625, 1.01171875, 3.3895314e38, 1e-45])
+    want = x.bfloat16().float()
+    got = ops.round_bf16(x.to(cuda))
+    assert torch.equal(got.cpu(), want)
+    nan = ops.round_bf16(torch.full((1, 1, 1, 4), float("nan"), device=cuda))
+    assert torch.isnan(nan).all()
+    buf = torch.zeros(2, 8, 7, 9, device=cuda)
+    buf[:, 2:7] = x.to(cuda)
+    ops.round_bf16(buf[:, 2:7], out=buf[:, 2:7])  # in place on a channel slice
+    assert torch.equal(buf[:, 2:7].cpu(), want) and float(buf[:, :2].abs().max()) == 0.0 and float(buf[:, 7:].abs().max()) == 0.0
+
+
 def test_refine_pieces(cuda):
     from irr_b200 import ops
     fl = torch.from_numpy(rs(61, (2, 2, 14, 22)))

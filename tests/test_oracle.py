@@ -161,3 +161,21 @@ def test_oracle_bit_exact_vs_live_reference():
         torch.Tensor.cuda = saved
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
+
+
+def test_oracle_bf16_feature_switch():
+    """BASELINE config 5: feature_bf16 rounds the pyramid features (not the images) to bf16 values; default off = the
+    reference's fp32 path, bit for bit unchanged."""
+    p = O.synthetic_params("IRR_PWC", seed=1234, gain=0.7)
+    i1, i2, _ = O.synthetic_pair(1, 64, 96, seed=9, max_flow=4.0)
+    with torch.no_grad():
+        a = O.irr_pwc_forward(p, i1, i2)
+        b = O.irr_pwc_forward(p, i1, i2, feature_bf16=False)
+        rec = {}
+        c = O.irr_pwc_forward(p, i1, i2, feature_bf16=True, record=rec)
+    assert torch.equal(a["flow"], b["flow"]) and torch.equal(a["occ"], b["occ"])
+    assert not torch.equal(a["flow"], c["flow"])
+    assert O.epe(a["flow"], c["flow"]).item() < 0.5          # a perturbation, not a different answer
+    x = rec["l2.x1"]
+    assert torch.equal(x, x.bfloat16().float())               # features carry bf16 values
+    assert torch.equal(rec["l6.x1"], i1)                      # the image level is not cast
