@@ -131,6 +131,24 @@ def gen_modules():
     print("modules.npz", len(cases))
 
 
+def gen_family():
+    """Eval outputs of the six remaining PWC-family classes through the reference's own modules."""
+    cases = {}
+    H, W = 64, 128
+    for name in O.FAMILY:
+        m = getattr(models, name)(None).eval()
+        p = O.synthetic_params(name, seed=1234, gain=0.7)
+        m.load_state_dict(p)
+        i1, i2, gt = O.synthetic_pair(1, H, W, seed=11, max_flow=5.0)
+        with torch.no_grad():
+            out = m({"input1": i1, "input2": i2})
+        for k, v in out.items():
+            cases[f"{name}__{k}"] = v.numpy()
+    cases["meta"] = np.array([1234, 11, 1, H, W])
+    np.savez_compressed(os.path.join(OUT, "family.npz"), **cases)
+    print("family.npz", len(cases))
+
+
 def gen_losses():
     """Eval-branch outputs of the reference's losses.py on oracle/losses_oracle.synthetic_eval_case inputs."""
     import losses as ref_losses
@@ -153,13 +171,14 @@ def gen_losses():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "losses":
-        gen_losses()
+    if len(sys.argv) > 1 and sys.argv[1] in ("losses", "family"):
+        {"losses": gen_losses, "family": gen_family}[sys.argv[1]]()
         sys.exit(0)
     gen_cost_volume()
     gen_warp()
     gen_modules()
     gen_models()
+    gen_family()
     gen_losses()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -345,7 +345,104 @@ def pwcnet_irr_occ_bi_forward(p: Params, img1, img2, div_flow=0.05, record: Opti
     return {"flow": resize_ac(flow_f, img1) * (1.0 / div_flow), "occ": resize_ac(occ_f, img1)}
 
 
+
+# The six remaining ablation classes of the PWC family.  One restatement parameterised by the three
+# switches the reference spells out in six files:
+#   irr : shared estimators + conv_1x1 + rescale_flow, context at every level      (pwcnet_irr*.py) vs per-level
+#         estimators on cat[corr, x, flow], context only at the output level       (pwcnet.py, pwcnet_bi/occ/occ_bi.py)
+#   bi  : forward and backward flow with the same weights                          (*_bi.py)
+#   occ : an occlusion branch next to the flow branch                              (*_occ*.py)
+FAMILY = {"PWCNet_bi": (False, True, False), "PWCNet_occ": (False, False, True), "PWCNet_occ_bi": (False, True, True),
+          "PWCNet_irr": (True, False, False), "PWCNet_irr_bi": (True, True, False), "PWCNet_irr_occ": (True, False, True)}
+
+
+def pwc_family_forward(model: str, p: Params, img1, img2, div_flow=0.05, record: Optional[dict] = None):
+    """Eval-mode forwards of models/pwcnet_bi.py:41-109, pwcnet_occ.py:49-117, pwcnet_occ_bi.py:49-132,
+    pwcnet_irr.py:43-97, pwcnet_irr_bi.py:43-111, pwcnet_irr_occ.py:47-112 — as executed, including
+    pwcnet_occ_bi.py:103, which feeds x1 (not x2) to the BACKWARD occlusion estimator."""
+    irr, bi, occ = FAMILY[model]
+    B, _, Him, Wim = img1.shape
+    pyr1 = feature_pyramid(p, img1) + [img1]
+    pyr2 = feature_pyramid(p, img2) + [img2]
+    h0, w0 = pyr1[0].shape[2:]
+    z = lambda c: torch.zeros(B, c, h0, w0, dtype=img1.dtype, device=img1.device)
+    flow_f, flow_b, occ_f, occ_b = z(2), z(2), z(1), z(1)
+    rec = (lambda k, v: record.__setitem__(k, v.clone())) if record is not None else (lambda k, v: None)
+    occ_ctx = "occ_context_networks" if irr else "context_networks_occ"
+    for l, (x1, x2) in enumerate(zip(pyr1, pyr2)):
+        if l == 0:
+            x2w, x1w = x2, x1
+        else:
+            flow_f = resize_ac(flow_f, x1)
+            x2w = warp(x2, flow_f, Him, Wim, div_flow)
+            if bi:
+                flow_b = resize_ac(flow_b, x2)
+                x1w = warp(x1, flow_b, Him, Wim, div_flow)
+            if occ:
+                occ_f = resize_ac(occ_f, x1)
+                if bi:
+                    occ_b = resize_ac(occ_b, x2)
+        corr_f = F.leaky_relu(cost_volume(x1, x2w), LEAKY)
+        corr_b = F.leaky_relu(cost_volume(x2, x1w), LEAKY) if bi else None
+        rec(f"l{l}.corr_f", corr_f)
+        if irr:
+            hw = x1.shape[2:]
+            su_l, sv_l = flow_scales(hw, Him, Wim, div_flow, True)
+            su_g, sv_g = flow_scales(hw, Him, Wim, div_flow, False)
+            x1_1 = conv_block(p, f"conv_1x1.{l}", x1)
+            flow_f = scale_flow(flow_f, su_l, sv_l)
+            xi, res = dense_estimator(p, "flow_estimators", torch.cat([corr_f, x1_1, flow_f], 1))
+            flow_f = flow_f + res
+            flow_f = flow_f + context_net(p, "context_networks", torch.cat([xi, flow_f], 1))
+            flow_f = scale_flow(flow_f, su_g, sv_g)
+            if bi:
+                x2_1 = conv_block(p, f"conv_1x1.{l}", x2)
+                flow_b = scale_flow(flow_b, su_l, sv_l)
+                xi, res = dense_estimator(p, "flow_estimators", torch.cat([corr_b, x2_1, flow_b], 1))
+                flow_b = flow_b + res
+                flow_b = flow_b + context_net(p, "context_networks", torch.cat([xi, flow_b], 1))
+                flow_b = scale_flow(flow_b, su_g, sv_g)
+            if occ:  # pwcnet_irr_occ.py:92-97 (uni-directional only in this family: irr+occ+bi is PWCNet_irr_occ_bi)
+                xo, ores = dense_estimator(p, "occ_estimators", torch.cat([corr_f, x1_1, occ_f], 1))
+                occ_f = occ_f + ores
+                occ_f = occ_f + context_net(p, occ_ctx, torch.cat([xo, occ_f], 1))
+        else:
+            in_f = corr_f if l == 0 else torch.cat([corr_f, x1, flow_f], 1)
+            xi_f, flow_f = dense_estimator(p, f"flow_estimators.{l}", in_f)
+            if bi:
+                in_b = corr_b if l == 0 else torch.cat([corr_b, x2, flow_b], 1)
+                xi_b, flow_b = dense_estimator(p, f"flow_estimators.{l}", in_b)
+            if occ:
+                io_f = corr_f if l == 0 else torch.cat([corr_f, x1, occ_f], 1)
+                xo_f, occ_f = dense_estimator(p, f"occ_estimators.{l}", io_f)
+                if bi:  # pwcnet_occ_bi.py:103 — x1, as written
+                    io_b = corr_b if l == 0 else torch.cat([corr_b, x1, occ_b], 1)
+                    xo_b, occ_b = dense_estimator(p, f"occ_estimators.{l}", io_b)
+            if l == OUT_LEVEL:
+                flow_f = flow_f + context_net(p, "context_networks", torch.cat([xi_f, flow_f], 1))
+                if bi:
+                    flow_b = flow_b + context_net(p, "context_networks", torch.cat([xi_b, flow_b], 1))
+                if occ:
+                    occ_f = occ_f + context_net(p, occ_ctx, torch.cat([xo_f, occ_f], 1))
+                    if bi:
+                        occ_b = occ_b + context_net(p, occ_ctx, torch.cat([xo_b, occ_b], 1))
+        rec(f"l{l}.flow_f", flow_f)
+        if bi:
+            rec(f"l{l}.flow_b", flow_b)
+        if occ:
+            rec(f"l{l}.occ_f", occ_f)
+        if l == OUT_LEVEL:
+            break
+    out = {"flow": resize_ac(flow_f, img1) * (1.0 / div_flow)}
+    if occ:
+        out["occ"] = resize_ac(occ_f, img1)
+    return out
+
+
 FORWARDS = {"IRR_PWC": irr_pwc_forward, "PWCNet": pwcnet_forward, "PWCNet_irr_occ_bi": pwcnet_irr_occ_bi_forward}
+for _name in FAMILY:
+    FORWARDS[_name] = (lambda name: (lambda p, a, b, div_flow=0.05, record=None:
+                                     pwc_family_forward(name, p, a, b, div_flow, record)))(_name)
 
 
 # --------------------------------------------------------------------------- parameters / synthetic data
@@ -377,10 +474,23 @@ def param_shapes(model: str) -> Dict[str, tuple]:
             add(f"{prefix}.convs.{i}", chs[i], chs[i + 1])
 
     dim_corr = (2 * SEARCH + 1) ** 2
-    if model == "PWCNet":
+    if model in ("PWCNet", "PWCNet_bi", "PWCNet_occ", "PWCNet_occ_bi"):  # per-level estimators (pwcnet.py:23-37 ...)
         for l, ch in enumerate(PYR_CHS[::-1][:OUT_LEVEL + 1]):
             dense(f"flow_estimators.{l}", dim_corr if l == 0 else dim_corr + ch + 2, 2)
+            if "occ" in model:
+                dense(f"occ_estimators.{l}", dim_corr if l == 0 else dim_corr + ch + 1, 1)
         ctx("context_networks", dim_corr + 32 + 2 + 448 + 2, 2)
+        if "occ" in model:
+            ctx("context_networks_occ", dim_corr + 32 + 1 + 448 + 1, 1)
+        return s
+    if model in ("PWCNet_irr", "PWCNet_irr_bi", "PWCNet_irr_occ"):  # shared estimators, five 1x1 convs
+        dense("flow_estimators", dim_corr + 34, 2)
+        ctx("context_networks", dim_corr + 34 + 448 + 2, 2)
+        if model == "PWCNet_irr_occ":
+            dense("occ_estimators", dim_corr + 33, 1)
+            ctx("occ_context_networks", dim_corr + 33 + 448 + 1, 1)
+        for l, c in enumerate([196, 128, 96, 64, 32]):
+            add(f"conv_1x1.{l}", c, 32, 1)
         return s
     dense("flow_estimators", dim_corr + 34, 2)
     ctx("context_networks", dim_corr + 34 + 448 + 2, 2)

@@ -185,6 +185,30 @@ def test_other_models_end_to_end(cuda, golden_dir, name, hw):
     assert e <= 2e-2 * scale
 
 
+@pytest.mark.parametrize("name", sorted(O.FAMILY))
+def test_family_models_end_to_end(cuda, golden_dir, conv_math, name):
+    """The six remaining PWC-family classes on the CUDA path vs the oracle and the reference-generated
+    golden output, even and odd sizes (the odd one only against the oracle)."""
+    if conv_math == "3xtf32":
+        pytest.skip("family models run in the default (3xF16) and the fp32 conv math")
+    m, p = build(name, cuda)
+    g = np.load(f"{golden_dir}/family.npz")
+    for (H, W, seed, mf) in [(64, 128, 11, 5.0), (94, 156, 12, 5.0)]:
+        i1, i2, gt = O.synthetic_pair(1, H, W, seed=seed, max_flow=mf)
+        with torch.no_grad():
+            ref = O.FORWARDS[name](p, i1, i2)
+            got = m({"input1": i1.to(cuda), "input2": i2.to(cuda)})
+        assert set(got) == set(ref)
+        d, e = _report(f"{name} {H}x{W} vs oracle(CPU)", got, ref, gt)
+        scale = max(1.0, ref["flow"].abs().max().item())
+        assert e <= 2e-2 * scale
+        if "occ" in ref:
+            assert (got["occ"].cpu() - ref["occ"]).abs().mean().item() <= 2e-2 * max(1.0, ref["occ"].abs().max().item())
+        if (H, W) == (64, 128):
+            gold = torch.from_numpy(g[f"{name}__flow"])
+            assert O.epe(got["flow"].cpu(), gold).item() <= 2e-2 * scale
+
+
 def test_other_models_teacher_forced(cuda):
     """Per-level record comparison for PWCNet_irr_occ_bi and PWCNet: level-l outputs given bit-close level inputs.
     Level 0 and 1 have no upstream mask chaos, so they are compared at 1e-4 directly."""

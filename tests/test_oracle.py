@@ -179,3 +179,48 @@ def test_oracle_bf16_feature_switch():
     x = rec["l2.x1"]
     assert torch.equal(x, x.bfloat16().float())               # features carry bf16 values
     assert torch.equal(rec["l6.x1"], i1)                      # the image level is not cast
+
+
+@pytest.mark.parametrize("name", sorted(O.FAMILY))
+def test_family_oracle_vs_golden(golden_dir, name):
+    """The six remaining PWC-family forwards: oracle restatement vs outputs generated from the
+    reference's own classes (oracle/gen_golden.py family).  Host-to-host noise bound as for the other models (F5)."""
+    g = np.load(f"{golden_dir}/family.npz")
+    seed_p, seed_i, B, H, W = [int(v) for v in g["meta"]]
+    p = O.synthetic_params(name, seed=seed_p, gain=0.7)
+    i1, i2, _ = O.synthetic_pair(B, H, W, seed=seed_i, max_flow=5.0)
+    with torch.no_grad():
+        out = O.FORWARDS[name](p, i1, i2)
+    assert set(out) == {k.split("__")[1] for k in g.files if k.startswith(name + "__")}
+    for k, v in out.items():
+        ref = torch.from_numpy(g[f"{name}__{k}"])
+        assert v.shape == ref.shape
+        if k == "flow":
+            assert O.epe(v, ref).item() <= 2e-2
+        else:
+            assert (v - ref).abs().mean().item() <= 2e-2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted (GPU box)")
+@pytest.mark.parametrize("name", sorted(O.FAMILY))
+def test_family_oracle_bit_exact_vs_live_reference(name):
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    saved = getattr(torch.Tensor, "cuda")
+    torch.Tensor.cuda = lambda self, *a, **k: self  # the reference hard-codes .cuda()
+    try:
+        import models
+        m = getattr(models, name)(None).eval()
+        p = O.synthetic_params(name, seed=4321, gain=0.7)
+        assert set(m.state_dict()) == set(p)
+        m.load_state_dict(p)
+        i1, i2, _ = O.synthetic_pair(1, 64, 64, seed=13, max_flow=4.0)
+        with torch.no_grad():
+            ref = m({"input1": i1, "input2": i2})
+            got = O.FORWARDS[name](p, i1, i2)
+        assert set(ref) == set(got)
+        for k in ref:
+            assert torch.equal(ref[k], got[k]), (name, k)
+    finally:
+        torch.Tensor.cuda = saved
