@@ -190,3 +190,33 @@ def test_harness_evaluate_matches_reference_moving_average(cuda):
     assert abs(got["epe"] - want["epe"] / n) <= 2e-3          # forward parity tolerance (EPE of the flows <= 2e-2 px)
     assert abs(got["F1"] - want["F1"] / n) <= 2e-2
     assert harness.evaluate(mal, []) == {}
+
+
+@pytest.mark.gpu
+def test_pipelined_inference_matches_direct_calls(cuda):
+    """harness.PipelinedInference: a stream of DIFFERENT batches through the double-buffered, overlapped loop returns, in
+    order, exactly what a direct model call returns for each batch (graph replay == eager launches, same kernels)."""
+    import irr_b200
+    from irr_b200 import harness
+    p = O.synthetic_params("IRR_PWC", seed=1234, gain=0.7)
+    m = irr_b200.IRR_PWC(None)
+    irr_b200.load_state_dict_strict(m, p)
+    m = m.to(cuda).eval()
+    H, W, B, n = 64, 96, 2, 5
+    runner = harness.PipelinedInference(m, B, H, W, cuda)
+    hosts, outs = [], []
+    for i in range(n):
+        i1, i2, _ = O.synthetic_pair(B, H, W, seed=40 + i, max_flow=4.0)
+        hosts.append((i1.pin_memory(), i2.pin_memory()))
+        outs.append((torch.empty(B, 2, H, W).pin_memory(), torch.empty(B, 1, H, W).pin_memory()))
+    for (h1, h2), (of, oo) in zip(hosts, outs):
+        runner.submit(h1, h2, of, oo)
+    runner.sync()
+    for (h1, h2), (of, oo) in zip(hosts, outs):
+        with torch.no_grad():
+            ref = m({"input1": h1.to(cuda), "input2": h2.to(cuda)})
+        # not torch.equal: the rolling conv kernel's three MMA issuers accumulate into one TMEM accumulator in issue
+        # order, which varies run to run (last-ulp differences, DESIGN.md §4.2); a wrong / stale batch would be O(1) off
+        assert (of - ref["flow"].cpu()).abs().max().item() <= 1e-4
+        assert (oo - ref["occ"].cpu()).abs().max().item() <= 1e-4
+    assert (outs[0][0] - outs[1][0]).abs().max().item() > 1e-2   # the batches really differ
