@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--math", default=os.environ.get("IRR_MATH", "auto"), choices=["auto", "fp32", "3xtf32", "tf32", "3xf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--serial-e2e", action="store_true", help="e2e loop without copy/compute overlap")
+    ap.add_argument("--no-pruned", action="store_true", help="skip the secondary eval_prune_dead measurement")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -296,6 +297,34 @@ def main():
     ms_e2e = e0.elapsed_time(e1)
     e2e_epe_check = float(torch.norm(oh_f[(args.steps - 1) & 1] - out["flow"].cpu(), p=2, dim=1).max())
 
+    # ---- secondary figure (never the headline): the same forward with the eval-dead backward-occlusion chain pruned
+    # (IRR_PWC.eval_prune_dead): identical outputs, fewer layers.  `value` above is the FULL forward.
+    pruned = None
+    if not args.no_pruned and graph is not None:
+        model.eval_prune_dead = True
+        try:
+            for _ in range(2):
+                model(inp)
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                out2 = model(inp)
+            for _ in range(args.warmup):
+                g2.replay()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(args.steps):
+                g2.replay()
+            p1.record()
+            barrier()
+            ms_p = p0.elapsed_time(p1)
+            pruned = {"ms": ms_p, "max_abs_flow_vs_full": float((out2["flow"] - out["flow"]).abs().max()),
+                      "max_abs_occ_vs_full": float((out2["occ"] - out["occ"]).abs().max())}
+            del g2, out2
+        finally:
+            model.eval_prune_dead = False
+
     # ---- per-kernel timing pass (eager, CUDA events on the launching stream around every launch)
     # (single stream: with the flow / occlusion branches overlapped on two streams per-launch times are not additive)
     from irr_b200 import IRR_PWC as _irr_mod
@@ -324,6 +353,8 @@ def main():
     epe_local = torch.norm(out["flow"] - gtc.to(dev), p=2, dim=1).mean(dim=(1, 2))
     epe_all = gather_metric(epe_local, B * world)
     ms, ms_e2e = max_over_ranks(ms, dev), max_over_ranks(ms_e2e, dev)
+    if pruned is not None:
+        pruned["ms"] = max_over_ranks(pruned["ms"], dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -398,6 +429,11 @@ def main():
         "roofline_corr_levels": levels[:6],
         "roofline_conv": roof_conv,
         "cpu_baseline": cpu,
+        "eval_pruned": None if pruned is None else {
+            "value": pairs / (pruned["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": pruned["ms"] / args.steps,
+            "max_abs_flow_vs_full": pruned["max_abs_flow_vs_full"], "max_abs_occ_vs_full": pruned["max_abs_occ_vs_full"],
+            "note": "SECONDARY, not the headline: same outputs with the eval-dead backward occlusion chain pruned "
+                    "(IRR_PWC.eval_prune_dead); `value` is the full reference-equivalent forward"},
         "metric_reduction": {"epe_vs_synthetic_gt_mean": float(epe_all.mean()), "samples": int(epe_all.numel()),
                              "collective": "nccl all_gather" if dist is not None else "none (1 GPU)"},
     }

@@ -84,6 +84,13 @@ class PWCNet(nn.Module):
         # BASELINE config 5 ("mixed bf16 features"): "bf16" rounds the feature pyramid to bf16 values before the warp /
         # correlation / 1x1 convs (a capability the fp32-only reference does not have; default = the reference's fp32)
         self.feature_dtype = "fp32"
+        # Dead-branch elimination for the eval forward (off by default = the reference's executed work, layer for
+        # layer).  In eval mode the reference returns only flow_f and occ_f (IRR_PWC.py:176-184); nothing that feeds
+        # them reads the BACKWARD occlusion chain: occ_b enters only its own estimator / context / refinement /
+        # up-sampling at the next level (:117-123, :141-145, :172).  With ``eval_prune_dead`` the occlusion branch runs
+        # on the forward rows only (the backward FLOW chain stays: flow_b is warped into the level-5/6 occlusion
+        # up-sampler, :157) — same outputs, ~30 % fewer conv FLOPs.
+        self.eval_prune_dead = False
         initialize_msra(self.modules())
 
     def set_feature_dtype(self, dtype: str):
@@ -110,7 +117,8 @@ class PWCNet(nn.Module):
 
         # estimator input buffers: [448 dense outputs | corr 81 | x_1by1 32 | flow 2 or occ 1 | est 2 or 1]
         buf_f = torch.empty((B2, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
-        buf_o = torch.empty((B2, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
+        BO = B if self.eval_prune_dead else B2   # rows the occlusion branch runs on
+        buf_o = torch.empty((BO, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
         corr = buf_f[:, 448:529]
         if l == 0:  # IRR_PWC.py:78-80,90-95 — no warp at the coarsest level
             ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
@@ -121,10 +129,10 @@ class PWCNet(nn.Module):
             self.conv_1x1[l](feat, out=x1by1)
         else:
             ops.scale_channels(feat, out=x1by1)
-        ops.scale_channels(buf_f[:, 448:561], out=buf_o[:, 448:561])  # shared [corr | x_1by1] block
+        ops.scale_channels(buf_f[:BO, 448:561], out=buf_o[:, 448:561])  # shared [corr | x_1by1] block
         su_l, sv_l = flow_scales(h, w, df, width_im, height_im, True)
         ops.scale_channels(flow_up, out=buf_f[:, 561:563], s_even=su_l, s_odd=sv_l)  # :105-106 to_local
-        ops.scale_channels(occ_up, out=buf_o[:, 561:562])
+        ops.scale_channels(occ_up[:BO], out=buf_o[:, 561:562])
         rec("corr", corr); rec("x_1by1", x1by1)
 
         # The flow branch (:108-114) and the occlusion branch (:117-123) are independent until the refinement: they run
@@ -169,12 +177,15 @@ class PWCNet(nn.Module):
 
     def refine_occ_stage(self, occ_cont, x1by1, flow, height_im, width_im):
         """IRR_PWC.py:141-145: occ = RefineOcc(occ_cont, x_1by1, x_1by1 - warp(other x_1by1, flow))."""
-        B2, _, h, w = occ_cont.shape
-        B = B2 // 2
-        ro_in = torch.empty((B2, 65, h, w), dtype=torch.float32, device=occ_cont.device)
+        BO, _, h, w = occ_cont.shape
+        B = x1by1.shape[0] // 2
+        ro_in = torch.empty((BO, 65, h, w), dtype=torch.float32, device=occ_cont.device)
         ops.scale_channels(occ_cont, out=ro_in[:, 0:1])
-        ops.scale_channels(x1by1, out=ro_in[:, 1:33])
-        ops.warp(x1by1, flow, height_im, width_im, self._div_flow, minuend=x1by1, shift=B, out=ro_in[:, 33:65])
+        ops.scale_channels(x1by1[:BO], out=ro_in[:, 1:33])
+        if BO == 2 * B:
+            ops.warp(x1by1, flow, height_im, width_im, self._div_flow, minuend=x1by1, shift=B, out=ro_in[:, 33:65])
+        else:  # forward rows only (eval_prune_dead): x1_1by1 - warp(x2_1by1, flow_f)
+            ops.warp(x1by1[B:], flow[:B], height_im, width_im, self._div_flow, minuend=x1by1[:B], out=ro_in[:, 33:65])
         return self.refine_occ.gather(ro_in, occ_cont)
 
     def upsample_level(self, l, feat, flow, occ_prev, height_im, width_im, record=None):
@@ -182,17 +193,30 @@ class PWCNet(nn.Module):
         B2, C, h, w = feat.shape
         B = B2 // 2
         df = self._div_flow
-        x_in = torch.empty((B2, 11, h, w), dtype=torch.float32, device=feat.device)
-        ops.upsample_nearest2x(occ_prev, h, w, out=x_in[:, 0:1])
-        if l != self.num_levels - 1:  # :160-164
-            self.conv_1x1_1(feat, out=x_in[:, 1:4])
-            xw = ops.warp(feat, flow, height_im, width_im, df, shift=B)
-            self.conv_1x1_1(xw, out=x_in[:, 4:7])
+        if occ_prev.shape[0] == B:  # eval_prune_dead: forward rows only (IRR_PWC.py:155,157,172 for occ_f)
+            x_in = torch.empty((B, 11, h, w), dtype=torch.float32, device=feat.device)
+            ops.upsample_nearest2x(occ_prev, h, w, out=x_in[:, 0:1])
+            if l != self.num_levels - 1:
+                self.conv_1x1_1(feat[:B], out=x_in[:, 1:4])
+                xw = ops.warp(feat[B:], flow[:B], height_im, width_im, df)
+                self.conv_1x1_1(xw, out=x_in[:, 4:7])
+            else:
+                ops.scale_channels(feat[:B], out=x_in[:, 1:4])
+                ops.warp(feat[B:], flow[:B], height_im, width_im, df, out=x_in[:, 4:7])
+            ops.scale_channels(flow[:B], out=x_in[:, 7:9])
+            ops.warp(flow[B:], flow[:B], height_im, width_im, df, out=x_in[:, 9:11])  # flow_b warped by flow_f
         else:
-            ops.scale_channels(feat, out=x_in[:, 1:4])
-            ops.warp(feat, flow, height_im, width_im, df, shift=B, out=x_in[:, 4:7])
-        ops.scale_channels(flow, out=x_in[:, 7:9])
-        ops.warp(flow, flow, height_im, width_im, df, shift=B, out=x_in[:, 9:11])  # flow_b warped by flow_f, and v.v.
+            x_in = torch.empty((B2, 11, h, w), dtype=torch.float32, device=feat.device)
+            ops.upsample_nearest2x(occ_prev, h, w, out=x_in[:, 0:1])
+            if l != self.num_levels - 1:  # :160-164
+                self.conv_1x1_1(feat, out=x_in[:, 1:4])
+                xw = ops.warp(feat, flow, height_im, width_im, df, shift=B)
+                self.conv_1x1_1(xw, out=x_in[:, 4:7])
+            else:
+                ops.scale_channels(feat, out=x_in[:, 1:4])
+                ops.warp(feat, flow, height_im, width_im, df, shift=B, out=x_in[:, 4:7])
+            ops.scale_channels(flow, out=x_in[:, 7:9])
+            ops.warp(flow, flow, height_im, width_im, df, shift=B, out=x_in[:, 9:11])  # flow_b warped by flow_f, and v.v.
         occ = self.occ_shuffle_upsample.forward_into(x_in)
         if record is not None:
             record["occ"] = occ.clone()
