@@ -166,6 +166,15 @@ int irr_channel_l2norm_fwd(const float* x, long long x_bs, float* y, long long y
 int irr_refine_gather_fwd(const float* logits, long long logits_bs, const float* src, long long src_bs, float* out,
                           long long out_bs, int B, int C, int H, int W, irr_stream_t stream);
 
+/* §8(f).4 — backward of the cost volume for the PWC parameters (pad 4, k 1, md 4, stride 1/1): replaces
+ * correlation_cuda.backward -> correlation_backward_input1/_input2 (correlation_cuda.cc:86-163,
+ * correlation_cuda_kernel.cu:116-300).  grad_out: B x 81 x H x W; grad_f1 / grad_f2: B x C x H x W, either may be NULL.
+ *   grad_f1[b,c,y,x] = (1/C) sum_d grad_out[b,d,y,x] * f2[b,c,y+dy,x+dx]
+ *   grad_f2[b,c,y,x] = (1/C) sum_d grad_out[b,d,y-dy,x-dx] * f1[b,c,y-dy,x-dx]      (zero outside the image) */
+int irr_correlation_bwd(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* grad_out,
+                        long long go_bs, float* grad_f1, long long g1_bs, float* grad_f2, long long g2_bs, int B, int C,
+                        int H, int W, int max_disp, irr_stream_t stream);
+
 /* §8(f).1 — evaluation metrics of the reference's eval-mode losses (losses.py:8-10, 24-37, 634-636, 688-697), one
  * launch per batch, deterministic.  flow / target: B x 2 x H x W; valid, occ_logits, target_occ: B x 1 x H x W or NULL.
  * sums: B x 8 float64 = { S epe*valid, S valid, S outlier, S pred*true, S pred, S true, 0, 0 } with

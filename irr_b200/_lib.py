@@ -46,6 +46,7 @@ PROTOTYPES = {
     "irr_upsample_nearest2x_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_sub_spatial_mean_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
     "irr_channel_l2norm_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],
+    "irr_correlation_bwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_eval_metrics_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_fp],
     "irr_refine_gather_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
 }

@@ -304,3 +304,19 @@ def eval_metrics(flow, target, valid=None, occ_logits=None, target_occ=None):
     _launch("eval_metrics", None, _lib.load().irr_eval_metrics_fwd, pf, sf, pt, st, pv, sv, po, so, pq, sq,
             sums.data_ptr(), B, H, W, _stream())
     return sums
+
+
+def correlation_backward(f1, f2, grad_out, need_f1: bool = True, need_f2: bool = True, max_disp: int = 4):
+    """(grad_f1, grad_f2) of ``correlation(f1, f2)`` (no LeakyReLU, no batch shift) — include/irr_b200.h
+    irr_correlation_bwd.  A gradient that is not needed is returned as None and not computed."""
+    B, C, H, W = f1.shape
+    D = (2 * max_disp + 1) ** 2
+    assert f2.shape == f1.shape and tuple(grad_out.shape) == (B, D, H, W)
+    g1 = torch.empty_like(f1) if need_f1 else None
+    g2 = torch.empty_like(f2) if need_f2 else None
+    p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pg, sg = _v(grad_out, "grad_out")
+    q1, t1 = _v(g1, "grad_f1") if g1 is not None else (None, 0)
+    q2, t2 = _v(g2, "grad_f2") if g2 is not None else (None, 0)
+    _launch("correlation_bwd", (B, C, H, W), _lib.load().irr_correlation_bwd, p1, s1, p2, s2, pg, sg, q1, t1, q2, t2, B, C,
+            H, W, max_disp, _stream())
+    return g1, g2

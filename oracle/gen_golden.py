@@ -149,6 +149,24 @@ def gen_family():
     print("family.npz", len(cases))
 
 
+def gen_corr_grad():
+    """Gradients of the reference's own (differentiable) compute_cost_volume, pwc_modules.py:42-62, for a seeded
+    upstream gradient — the values correlation_cuda.backward (correlation_cuda_kernel.cu:116-300) is defined to return."""
+    cases = {}
+    par = {"pad_size": 4, "kernel_size": 1, "max_disp": 4, "stride1": 1, "stride2": 1, "corr_multiply": 1}
+    for si, shape in enumerate([(1, 5, 9, 13), (2, 16, 17, 40), (1, 32, 24, 64)]):
+        f1 = rs_tensor(500 + si, shape).requires_grad_(True)
+        f2 = rs_tensor(520 + si, shape).requires_grad_(True)
+        go = rs_tensor(540 + si, (shape[0], 81, shape[2], shape[3]))
+        out = pwc.compute_cost_volume(f1, f2, par)
+        out.backward(go)
+        cases[f"g1__{si}"] = f1.grad.numpy()
+        cases[f"g2__{si}"] = f2.grad.numpy()
+        cases[f"shape__{si}"] = np.array(shape)
+    np.savez_compressed(os.path.join(OUT, "corr_grad.npz"), **cases)
+    print("corr_grad.npz", len(cases))
+
+
 def gen_losses():
     """Eval-branch outputs of the reference's losses.py on oracle/losses_oracle.synthetic_eval_case inputs."""
     import losses as ref_losses
@@ -171,14 +189,15 @@ def gen_losses():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    if len(sys.argv) > 1 and sys.argv[1] in ("losses", "family"):
-        {"losses": gen_losses, "family": gen_family}[sys.argv[1]]()
+    if len(sys.argv) > 1 and sys.argv[1] in ("losses", "family", "corr_grad"):
+        {"losses": gen_losses, "family": gen_family, "corr_grad": gen_corr_grad}[sys.argv[1]]()
         sys.exit(0)
     gen_cost_volume()
     gen_warp()
     gen_modules()
     gen_models()
     gen_family()
+    gen_corr_grad()
     gen_losses()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

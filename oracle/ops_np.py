@@ -146,3 +146,24 @@ def resize_ac_np(x: np.ndarray, oh: int, ow: int) -> np.ndarray:
     top = (w0l * a + w1l * b).astype(f32)
     bot = (w0l * c + w1l * d).astype(f32)
     return (h0l[:, None] * top + h1l[:, None] * bot).astype(f32)
+
+
+def cost_volume_backward_np(f1: np.ndarray, f2: np.ndarray, grad_out: np.ndarray, max_disp: int = 4):
+    """Backward of cost_volume_np == what correlation_backward_input1 / _input2 return for the PWC parameters
+    (correlation_cuda_kernel.cu:116-300; sumelems = C there, :195/:289):
+        grad_f1[b,c,y,x] = (1/C) sum_d g[b,d,y,x] * f2[b,c,y+dy,x+dx]
+        grad_f2[b,c,y,x] = (1/C) sum_d g[b,d,y-dy,x-dx] * f1[b,c,y-dy,x-dx]
+    float64 accumulation (checker only)."""
+    B, C, H, W = f1.shape
+    md, nd = max_disp, 2 * max_disp + 1
+    f1p = np.pad(f1.astype(np.float64), ((0, 0), (0, 0), (md, md), (md, md)))
+    f2p = np.pad(f2.astype(np.float64), ((0, 0), (0, 0), (md, md), (md, md)))
+    g = grad_out.astype(np.float64)
+    g1 = np.zeros((B, C, H, W), np.float64)
+    g2p = np.zeros((B, C, H + 2 * md, W + 2 * md), np.float64)
+    for dyi in range(nd):
+        for dxi in range(nd):
+            gd = g[:, dyi * nd + dxi][:, None]                      # (B, 1, H, W)
+            g1 += gd * f2p[:, :, dyi:dyi + H, dxi:dxi + W]
+            g2p[:, :, dyi:dyi + H, dxi:dxi + W] += gd * f1p[:, :, md:md + H, md:md + W]
+    return (g1 / C).astype(np.float32), (g2p[:, :, md:md + H, md:md + W] / C).astype(np.float32)

@@ -234,6 +234,31 @@ def test_resize_scale_nearest(cuda, golden_dir):
         assert (got - ref).abs().max().item() <= 5e-6  # CPU vs CUDA-order bilinear (align_corners=False) differ by ulps
 
 
+@pytest.mark.parametrize("si", [0, 1, 2])
+def test_correlation_backward_golden(cuda, golden_dir, si):
+    """irr_correlation_bwd vs the gradients of the reference's compute_cost_volume (golden) and the numpy oracle; through
+    the autograd Function, including a one-sided gradient."""
+    import irr_b200
+    from irr_b200 import ops
+    g = np.load(f"{golden_dir}/corr_grad.npz")
+    shape = tuple(int(v) for v in g[f"shape__{si}"])
+    rs = lambda seed, shp: torch.from_numpy(np.random.RandomState(seed).standard_normal(shp).astype("float32"))
+    f1, f2, go = rs(500 + si, shape), rs(520 + si, shape), rs(540 + si, (shape[0], 81, shape[2], shape[3]))
+    a = f1.to(cuda).requires_grad_(True)
+    b = f2.to(cuda).requires_grad_(True)
+    corr = irr_b200.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+    out = corr(a, b)
+    out.backward(go.to(cuda))
+    assert np.abs(a.grad.cpu().numpy() - g[f"g1__{si}"]).max() <= 2e-6
+    assert np.abs(b.grad.cpu().numpy() - g[f"g2__{si}"]).max() <= 2e-6
+    o1, o2 = N.cost_volume_backward_np(f1.numpy(), f2.numpy(), go.numpy())
+    assert np.abs(a.grad.cpu().numpy() - o1).max() <= 2e-6 and np.abs(b.grad.cpu().numpy() - o2).max() <= 2e-6
+    g1, none = ops.correlation_backward(f1.to(cuda), f2.to(cuda), go.to(cuda), need_f1=True, need_f2=False)
+    assert none is None and torch.equal(g1, a.grad)
+    with pytest.raises(NotImplementedError):
+        irr_b200.Correlation(20, 1, 20, 1, 2)(a, b)
+
+
 def test_round_bf16(cuda):
     """irr_round_bf16_fwd == x.bfloat16().float() bit for bit (RNE, ties, subnormals, inf, NaN), slices, in place."""
     from irr_b200 import ops

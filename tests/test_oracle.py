@@ -224,3 +224,15 @@ def test_family_oracle_bit_exact_vs_live_reference(name):
             assert torch.equal(ref[k], got[k]), (name, k)
     finally:
         torch.Tensor.cuda = saved
+
+
+@pytest.mark.parametrize("si", [0, 1, 2])
+def test_cost_volume_backward_oracle_vs_reference_autograd(golden_dir, si):
+    """§8(f).4: the numpy backward vs gradients of the reference's own differentiable compute_cost_volume
+    (tests/golden/corr_grad.npz, oracle/gen_golden.py corr_grad)."""
+    g = np.load(f"{golden_dir}/corr_grad.npz")
+    shape = tuple(int(v) for v in g[f"shape__{si}"])
+    rs = lambda seed, shp: np.random.RandomState(seed).standard_normal(shp).astype("float32")
+    f1, f2, go = rs(500 + si, shape), rs(520 + si, shape), rs(540 + si, (shape[0], 81, shape[2], shape[3]))
+    g1, g2 = N.cost_volume_backward_np(f1, f2, go)
+    assert np.abs(g1 - g[f"g1__{si}"]).max() <= 2e-6 and np.abs(g2 - g[f"g2__{si}"]).max() <= 2e-6
