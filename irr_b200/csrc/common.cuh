@@ -119,6 +119,20 @@ __device__ __forceinline__ float grid_base(const float* lin, float step, int i, 
   return __fadd_rn(-1.0f, __fmul_rn(step, (float)i));
 }
 
+// Correctly rounded a / b for a CONSTANT divisor b whose correctly rounded reciprocal rb = RN(1/b) was computed on the
+// host: q = RN(a*rb) is faithful, and each step q += RN(a - q*b) * rb (the residual is exact in one FMA) lands on RN(a/b)
+// (Markstein).  Five dependent FMA-pipe instructions instead of __fdiv_rn's ~15 + FCHK + slow-path branch — the grid
+// arithmetic of the warp is bit-sensitive (hard mask), so "close" is not good enough: the recipe is checked
+// against IEEE division on 56 M random operands (tests/test_oracle.py::test_constant_division_recipe) and bitwise
+// against torch through the warp tests.  Inf / NaN inputs give NaN instead of Inf: both mask the pixel out.
+__device__ __forceinline__ float div_const_rn(float a, float b, float rb) {
+  float q = __fmul_rn(a, rb);
+  float r = __fmaf_rn(-q, b, a);
+  q = __fmaf_rn(r, rb, q);
+  r = __fmaf_rn(-q, b, a);
+  return __fmaf_rn(r, rb, q);
+}
+
 // Unnormalised source coordinates for output pixel (y, x) with flow (u, v).
 __device__ __forceinline__ void sample_coords(const GridArgs& g, float u, float v, int x, int y, int W, int H,
                                               float& ix, float& iy) {
@@ -127,8 +141,8 @@ __device__ __forceinline__ void sample_coords(const GridArgs& g, float u, float 
     fx = __fmul_rn(__fmul_rn(__fmul_rn(u, 2.0f), g.rcp_x), g.rcp_div);
     fy = __fmul_rn(__fmul_rn(__fmul_rn(v, 2.0f), g.rcp_y), g.rcp_div);
   } else {
-    fx = __fdiv_rn(__fdiv_rn(__fmul_rn(u, 2.0f), g.den_x), g.div_flow);
-    fy = __fdiv_rn(__fdiv_rn(__fmul_rn(v, 2.0f), g.den_y), g.div_flow);
+    fx = div_const_rn(div_const_rn(__fmul_rn(u, 2.0f), g.den_x, g.rcp_x), g.div_flow, g.rcp_div);
+    fy = div_const_rn(div_const_rn(__fmul_rn(v, 2.0f), g.den_y, g.rcp_y), g.div_flow, g.rcp_div);
   }
   float gx = __fadd_rn(grid_base(g.lin_x, g.step_x, x, W), fx);
   float gy = __fadd_rn(grid_base(g.lin_y, g.step_y, y, H), fy);

@@ -236,3 +236,26 @@ def test_cost_volume_backward_oracle_vs_reference_autograd(golden_dir, si):
     f1, f2, go = rs(500 + si, shape), rs(520 + si, shape), rs(540 + si, (shape[0], 81, shape[2], shape[3]))
     g1, g2 = N.cost_volume_backward_np(f1, f2, go)
     assert np.abs(g1 - g[f"g1__{si}"]).max() <= 2e-6 and np.abs(g2 - g[f"g2__{si}"]).max() <= 2e-6
+
+
+def test_constant_division_recipe():
+    """csrc/common.cuh div_const_rn: q = RN(a*rb); twice q += RN(a - q*b)*rb with rb = RN(1/b) equals IEEE a/b bit for bit.
+    fp32 FMA emulated in float64 (the product of two fp32 is exact there and the residual cancels to few bits)."""
+    rng = np.random.default_rng(0)
+
+    def fma32(x, y, z):
+        return (x.astype(np.float64) * y.astype(np.float64) + z.astype(np.float64)).astype(np.float32)
+
+    def recipe(a, b):
+        rb = (np.float32(1.0) / b).astype(np.float32)
+        q = (a * rb).astype(np.float32)
+        for _ in range(2):
+            q = fma32(fma32(-q, b, a), rb, q)
+        return q
+    for b in (1023.0, 435.0, 1241.0, 374.0, 0.05, 3.0, 255.0, 7.0):
+        a = (rng.standard_normal(500_000) * rng.choice([1e-3, 0.1, 1, 10, 100, 1e4], 500_000)).astype(np.float32)
+        bb = np.full_like(a, np.float32(b))
+        assert np.array_equal((a / bb).astype(np.float32), recipe(a, bb)), b
+    a = (rng.standard_normal(1_000_000) * 10).astype(np.float32)
+    b = rng.uniform(0.01, 4096, 1_000_000).astype(np.float32)
+    assert np.array_equal((a / b).astype(np.float32), recipe(a, b))
