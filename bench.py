@@ -143,6 +143,32 @@ def cpu_forward_sample(steps, warmup, threads=None):
     return ts
 
 
+def torch_gpu_sample(params, i1, i2, dev, steps=2):
+    """"also time the reference on GPU (PyTorch ops, fp32, TF32 off) as the honest kernel to beat".
+    The reference itself is not on the box; its bit-exact restatement (oracle/irr_oracle.py) is device-agnostic torch
+    code, so run on `dev` it executes the reference's ATen / cuDNN op sequence (~16 k launches per forward).  Reported
+    baseline only (like cpu_baseline): bounded, after the timed regions.  Returns (pairs/s, output dict)."""
+    from oracle import irr_oracle as O
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        p = {k: v.to(dev) for k, v in params.items()}
+        a, b = i1.to(dev), i2.to(dev)
+        with torch.no_grad():
+            out = O.irr_pwc_forward(p, a, b)  # warm-up (cuDNN algorithm selection)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = O.irr_pwc_forward(p, a, b)
+            e1.record()
+            torch.cuda.synchronize()
+        return steps * a.shape[0] / (e0.elapsed_time(e1) * 1e-3), out
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -179,6 +205,7 @@ def main():
     ap.add_argument("--math", default=os.environ.get("IRR_MATH", "auto"), choices=["auto", "fp32", "3xtf32", "tf32", "3xf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--serial-e2e", action="store_true", help="e2e loop without copy/compute overlap")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the PyTorch-ops-on-GPU baseline (oracle on cuda)")
     ap.add_argument("--no-pruned", action="store_true", help="skip the secondary eval_prune_dead measurement")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     args = ap.parse_args()
@@ -400,6 +427,18 @@ def main():
                  "share_of_step": conv_ms / total_kernel_ms, "flop_per_step": conv_fl, "math": math_name}
 
     # ---- CPU baseline (bounded sample: one pair per step through the oracle on all host cores)
+    tgpu = None
+    if not args.no_torch_gpu:
+        try:
+            v, ref_out = torch_gpu_sample(O.synthetic_params("IRR_PWC", seed=1234, gain=0.7), i1c, i2c, dev)
+            tgpu = {"value": v, "unit": "pairs/s", "kind": "port on the GPU: the oracle's torch restatement of the reference "
+                    "forward run with PyTorch CUDA ops (cuDNN convs, fp32, TF32 off, eager)", "sample": f"2 x batch {B}",
+                    "epe_ours_vs_torch_gpu": float(O.epe(out["flow"], ref_out["flow"])),
+                    "max_abs_flow_ours_vs_torch_gpu": float((out["flow"] - ref_out["flow"]).abs().max())}
+            del ref_out
+        except Exception as ex:  # a reported baseline must never take the bench line down
+            tgpu = {"unavailable": repr(ex)[:200]}
+        torch.cuda.empty_cache()
     ts = cpu_forward_sample(args.cpu_baseline_steps, 1) if args.cpu_baseline_steps > 0 else []
     cpu = None
     if ts:
@@ -429,6 +468,7 @@ def main():
         "roofline_corr_levels": levels[:6],
         "roofline_conv": roof_conv,
         "cpu_baseline": cpu,
+        "torch_gpu_baseline": tgpu,
         "eval_pruned": None if pruned is None else {
             "value": pairs / (pruned["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": pruned["ms"] / args.steps,
             "max_abs_flow_vs_full": pruned["max_abs_flow_vs_full"], "max_abs_occ_vs_full": pruned["max_abs_occ_vs_full"],

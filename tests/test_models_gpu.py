@@ -178,6 +178,27 @@ def test_irr_eval_prune_dead_is_output_identical(irr_case, cuda):
     assert e <= 5e-3 and mo <= 5e-2   # (occ logits: ours-vs-oracle max-abs is 0.2-0.5 in the same tests)
 
 
+@pytest.mark.parametrize("name", ["IRR_PWC", "PWCNet_irr_occ_bi"])
+def test_full_size_sintel_shape_end_to_end(cuda, conv_math, name):
+    """BASELINE configs 3 and 4 at their full image size (436 x 1024; batch 2 instead of 8 / 32 so the CPU oracle finishes
+    in seconds — the batch only replicates the per-pair work): every pyramid level at the sizes the bench runs, against
+    the oracle, plus the size-independent properties: batch rows are independent (row 0 of a batch-2 run == a batch-1
+    run of the same pair, to the run-to-run noise) and finite everywhere."""
+    if conv_math != "3xf16":
+        pytest.skip("full-size run only in the default conv math")
+    m, p = build(name, cuda)
+    i1, i2, gt = O.synthetic_pair(2, 436, 1024, seed=3, max_flow=20.0)
+    with torch.no_grad():
+        ref = O.FORWARDS[name](p, i1, i2)
+        got = m({"input1": i1.to(cuda), "input2": i2.to(cuda)})
+        one = m({"input1": i1[:1].to(cuda), "input2": i2[:1].to(cuda)})
+    assert got["flow"].shape == (2, 2, 436, 1024) and torch.isfinite(got["flow"]).all() and torch.isfinite(got["occ"]).all()
+    d, e = _report(f"{name} 436x1024 b2 vs oracle(CPU)", got, ref, gt)
+    scale = max(1.0, ref["flow"].abs().max().item() / 50.0)
+    assert e <= 2e-2 * scale
+    assert O.epe(got["flow"][:1].cpu(), one["flow"].cpu()).item() <= 5e-3   # batch independence
+
+
 @pytest.mark.parametrize("feat", ["fp32", "bf16"])
 def test_irr_kitti_shape_end_to_end(cuda, conv_math, feat):
     """BASELINE config 5's shape (375 x 1242: level widths 621/311/156/78/39/20 — only two of them 16-byte aligned, so the
