@@ -228,7 +228,7 @@ def main():
 
     import irr_b200
     from irr_b200 import ops, pwc_modules
-    from oracle import irr_oracle as O  # parameters / synthetic inputs only (shared with the reference arm)
+    from irr_b200 import synthetic as O  # deterministic parameters / inputs (no oracle code on the timed path)
 
     math = {"fp32": ops.MATH_FP32_SIMT, "3xtf32": ops.MATH_TC_3XTF32, "tf32": ops.MATH_TC_TF32,
             "3xf16": ops.MATH_TC_3XF16}.get(args.math)

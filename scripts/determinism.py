@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, irr_b200
-from oracle import irr_oracle as O
+from irr_b200 import synthetic as O   # parameter / input generators
 dev = torch.device("cuda:0")
 H, W, B = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (64, 96, 2)
 m = irr_b200.IRR_PWC(None); irr_b200.load_state_dict_strict(m, O.synthetic_params("IRR_PWC", seed=1234, gain=0.7)); m = m.to(dev).eval()

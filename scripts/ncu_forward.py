@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import irr_b200
 from irr_b200 import ops, pwc_modules
-from oracle import irr_oracle as O   # parameter / input generators only
+from irr_b200 import synthetic as O   # parameter / input generators
 
 dev = torch.device("cuda:0")
 pwc_modules.set_conv_math({"fp32": 0, "3xtf32": 1, "tf32": 2, "3xf16": 3}[os.environ.get("IRR_MATH", "3xf16")])
