@@ -166,6 +166,50 @@ def test_warp_correlation_fused_equals_unfused(cuda):
     assert (fused.cpu() - ref).abs().max().item() <= 1e-4
 
 
+def test_cost_volume_full_size_properties(cuda):
+    """BASELINE config 3's largest correlation launch (2B=16, C=32, 109 x 256 — too big for the CPU oracle in a unit
+    test) through size-independent properties: displacement symmetry (exact: the same products in the same order),
+    linearity in f1, the fused warp == warp kernel + plain kernel, a strided sample of pixels against a
+    direct dot product, and the cp.async fallback kernel == the TMA kernel (exact)."""
+    import os
+    from irr_b200 import ops
+    B, C, H, W = 16, 32, 109, 256
+    g = torch.Generator(device="cpu").manual_seed(123)
+    f1 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    f2 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    g1 = torch.randn(B, C, H, W, generator=g).to(cuda)
+    a = ops.correlation(f1, f2)
+    # symmetry: corr(f1, f2)[dy, dx](y, x) == corr(f2, f1)[-dy, -dx](y + dy, x + dx)
+    b = ops.correlation(f2, f1)
+    for dy, dx in [(-4, -4), (0, 3), (2, -1), (4, 4), (0, 0)]:
+        ch, chm = (dy + 4) * 9 + (dx + 4), (-dy + 4) * 9 + (-dx + 4)
+        ys, ye = max(0, -dy), min(H, H - dy)
+        xs, xe = max(0, -dx), min(W, W - dx)
+        assert torch.equal(a[:, ch, ys:ye, xs:xe], b[:, chm, ys + dy:ye + dy, xs + dx:xe + dx]), (dy, dx)
+    # linearity in f1
+    lin = ops.correlation(2.5 * f1 + g1, f2)
+    assert (lin - (2.5 * a + ops.correlation(g1, f2))).abs().max().item() <= 2e-5
+    # fused warp == warp kernel followed by the plain kernel, for a smooth sub-pixel flow and for zero flow (which is
+    # NOT the identity at every size: the rounded linspace grid leaves some pixels with a weight sum < 1, SURVEY F4)
+    lo = torch.randn(B, 2, 3, 4, generator=g).to(cuda)
+    smooth = torch.nn.functional.interpolate(lo, size=[H, W], mode="bicubic", align_corners=True) * 0.4
+    for flow in (smooth, torch.zeros(B, 2, H, W, device=cuda)):
+        fused = ops.warp_correlation(f1, f2, flow, 436, 1024, 0.05, shift=B // 2)
+        unfused = ops.correlation(f1, ops.warp(f2, flow, 436, 1024, 0.05, shift=B // 2))
+        assert (fused - unfused).abs().max().item() <= 1e-6
+    # direct dot products at a strided sample of pixels / displacements
+    f2p = torch.nn.functional.pad(f2, (4, 4, 4, 4))
+    for (y, x, dy, dx) in [(0, 0, -4, -4), (0, 255, 4, 4), (108, 0, 4, -4), (54, 128, 1, -2), (108, 255, -3, 0), (7, 31, 0, 4)]:
+        want = (f1[:, :, y, x] * f2p[:, :, y + dy + 4, x + dx + 4]).sum(1) / C
+        assert (a[:, (dy + 4) * 9 + (dx + 4), y, x] - want).abs().max().item() <= 1e-5
+    # the cp.async fallback kernel computes the same sums in the same order
+    os.environ["IRR_CORR_NO_TMA"] = "1"
+    try:
+        assert torch.equal(ops.correlation(f1, f2), a)
+    finally:
+        del os.environ["IRR_CORR_NO_TMA"]
+
+
 # ------------------------------------------------------------------ conv
 CONV_CASES = [
     # (B, Cin, H, W, Cout, k, stride, dil)
