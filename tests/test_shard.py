@@ -47,3 +47,20 @@ def test_gather_metric_gloo_world2():
     for rank, full, t in res:
         assert full == [float(i) * 10.0 for i in range(7)]
         assert t == 2.0
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses bench.py's stdout: one JSON line, nothing else (library chatter is routed to stderr)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
