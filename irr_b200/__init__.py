@@ -20,7 +20,7 @@ from .pwcnet_irr import PWCNet as PWCNet_irr  # noqa: F401
 from .pwcnet_irr_bi import PWCNet as PWCNet_irr_bi  # noqa: F401
 from .pwcnet_irr_occ import PWCNet as PWCNet_irr_occ  # noqa: F401
 from .checkpoint import load_reference_checkpoint, load_state_dict_strict  # noqa: F401
-from .install import install  # noqa: F401
+from .install import install, patch_instances, uninstall  # noqa: F401
 
 MODELS = {"IRR_PWC": IRR_PWC, "PWCNet": PWCNet, "PWCNet_irr_occ_bi": PWCNet_irr_occ_bi, "PWCNet_bi": PWCNet_bi,
           "PWCNet_occ": PWCNet_occ, "PWCNet_occ_bi": PWCNet_occ_bi, "PWCNet_irr": PWCNet_irr,

@@ -2,7 +2,9 @@
 
 The reference saves ``{'epe':…, 'F1':…, 'epoch':…, 'state_dict': ModelAndLoss.state_dict()}`` (configuration.py:290-300);
 every key carries the ``_model.`` prefix because the saved module is ``ModelAndLoss`` (configuration.py:23,291).
-Plain floats are pickled next to the tensors, hence ``weights_only=False`` on torch >= 2.6."""
+The files hold only tensors, floats and ints, so they are read with ``weights_only=True`` (no arbitrary pickle code
+is executed — checkpoints are usually downloaded); ``trust=True`` is the explicit opt-in for a file that needs the
+full unpickler."""
 from __future__ import annotations
 
 import torch
@@ -29,8 +31,9 @@ def load_state_dict_strict(model, state_dict):
     return model
 
 
-def load_reference_checkpoint(model, path, map_location="cpu"):
-    """Returns the stats dict stored beside the weights (epe / F1 / outlier / epoch)."""
-    ck = torch.load(path, map_location=map_location, weights_only=False)
+def load_reference_checkpoint(model, path, map_location="cpu", trust: bool = False):
+    """Returns the stats dict stored beside the weights (epe / F1 / outlier / epoch).  ``trust=True`` unpickles with
+    ``weights_only=False`` (runs arbitrary code from the file: only for files you made yourself)."""
+    ck = torch.load(path, map_location=map_location, weights_only=not trust)
     load_state_dict_strict(model, ck["state_dict"])
     return {k: v for k, v in ck.items() if k != "state_dict"}

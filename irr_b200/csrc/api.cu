@@ -31,6 +31,11 @@ int check_launch(const char* fn) {
   return 0;
 }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

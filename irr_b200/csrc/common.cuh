@@ -13,6 +13,25 @@ void set_error(const char* fmt, ...);
 int fail_arg(const char* fn, const char* what);
 int check_launch(const char* fn);
 int sm_count();
+int current_device();  // cudaGetDevice(), -1 on failure
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: remember, per device, how far it
+// has been raised (one process may drive several GPUs — ADVICE r1).
+struct SmemAttrCache { size_t bytes[64]; };
+void set_error(const char* fmt, ...);
+template <typename Kern>
+static inline int ensure_dyn_smem(Kern kern, size_t smem, SmemAttrCache& cache, const char* fn) {
+  const int dev = current_device();
+  const bool cacheable = dev >= 0 && dev < 64;
+  if (cacheable && smem <= cache.bytes[dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu): %s", fn, smem, cudaGetErrorString(e));
+    return (int)e;
+  }
+  if (cacheable) cache.bytes[dev] = smem;
+  return 0;
+}
 
 #define IRR_REQUIRE(cond, fn, what) \
   do {                              \

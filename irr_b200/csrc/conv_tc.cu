@@ -497,15 +497,8 @@ int tc_pack(const float* w, void* out, int Cout, int Cin, int ks, int math, cuda
 
 template <int KS, int PASSES>
 static int launch_tc(const TcArgs& a, size_t smem, cudaStream_t st) {
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_smem = smem;
-  }
+  static SmemAttrCache attr = {};
+  if (int rc = ensure_dyn_smem(conv_tc_kernel<KS, PASSES>, smem, attr, "irr_conv2d_fwd")) return rc;
   long long items = ((a.M + TC_BM2 - 1) / TC_BM2) * a.n_tiles;
   int grid = (int)(items < sm_count() ? items : sm_count());  // persistent: one CTA per SM (TMEM: 512 columns each)
   conv_tc_kernel<KS, PASSES><<<grid, TC_THREADS2, smem, st>>>(a);

@@ -656,7 +656,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
 //     of row r-1, so each A stage feeds three MMA groups that differ only in weights and accumulator;
 //   * four output-row accumulators rotate through TMEM ([0,256): 4 x 64 columns); three MMA-issuing warps, one per ky,
 //     work on three different accumulators at once.  Accumulators are zeroed by the epilogue when it drains them
-//     (every MMA accumulates), so there is no first-MMA ordering between the issuers;
+//     (every MMA accumulates), so no issuer has to be "first"; the three tap-row groups of an output row are chained
+//     through completion tokens (ord) so that they are always summed ky = 0, 1, 2: bit-deterministic results;
 //   * the layer's nine weight images stay resident in shared memory; rows above/below the image arrive as TMA zeros,
 //     so every segment runs the same L+2 row schedule.
 // Roles: warps 0-7 producers (two groups of four on alternate rows, pixel = thread), 8-10 MMA issuers (ky), 11 loader,
@@ -696,6 +697,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
   const uint32_t w_full = bar0 + 8u * 36;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 38);
   float* bias_s = reinterpret_cast<float*>(bars + 40);       // 64 floats, 16-byte aligned
+  // tap-row order tokens: ord(ky, slot) completes when issuer ky's MMA group on accumulator `slot` has been EXECUTED;
+  // issuer ky+1 waits for it before adding its own group, so every output row is summed ky = 0, 1, 2 — always.
+  auto ord = [&](int ky, int s) { return bar0 + 8u * (72 + 4 * ky + s); };   // [72, 80)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long* ctr = (CTR && blockIdx.x == 0) ? h_ctr_ptr : nullptr;
@@ -706,6 +710,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     for (int s = 0; s < R_XS; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 4); }  // 4 warps of the owning group
     for (int s = 0; s < R_SA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 3); }
     for (int s = 0; s < 4; ++s) { mbar_init(acc_full(s), 3); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < 8; ++s) mbar_init(ord(s >> 2, s & 3), 1);
     mbar_init(w_full, 1);
     mbar_fence_init();
   }
@@ -834,7 +839,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
           H_T0();
           mbar_wait(a_full(sa), (uint32_t)((ca / R_SA) & 1));
           H_ACC(0);
-          if (valid && kx == 0) mbar_wait(acc_empty(slot), (uint32_t)((og >> 2) & 1));  // drained and zeroed
+          if (valid && kx == 0) {
+            mbar_wait(acc_empty(slot), (uint32_t)((og >> 2) & 1));  // drained and zeroed
+            // bit-determinism: the ky = 0 group of this output row (issued one staged row earlier by warp 8) must have
+            // been accumulated before ky = 1 adds to it, and ky = 1 before ky = 2.  The predecessor finished a whole
+            // producer row (~1600 clk) ago in steady state, so this wait is almost always already satisfied.
+            if (ky > 0) mbar_wait(ord(ky - 1, slot), (uint32_t)((og >> 2) & 1));
+          }
           h_fence_after();
           H_ACC(1);
           if (h_elect()) {
@@ -850,7 +861,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                 h_mma_ts(d_tmem, a_hi + 8, bd + 2, idesc, 1u);
               }
               h_commit(a_empty(sa));
-              if (kx == 2) h_commit(acc_full(slot));
+              if (kx == 2) {
+                if (ky < 2) h_commit(ord(ky, slot));
+                h_commit(acc_full(slot));
+              }
             } else {
               mbar_arrive(a_empty(sa));
             }
@@ -1083,15 +1097,8 @@ int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t 
 
 template <int KS, bool STAGED, bool CTR>
 static int launch_h16_(const CUtensorMap& map, const HArgs& a, size_t smem, cudaStream_t st) {
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_h16_kernel<KS, STAGED, CTR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_smem = smem;
-  }
+  static SmemAttrCache attr = {};
+  if (int rc = ensure_dyn_smem(conv_h16_kernel<KS, STAGED, CTR>, smem, attr, "irr_conv2d_fwd")) return rc;
   int grid = a.items < sm_count() ? a.items : sm_count();
   conv_h16_kernel<KS, STAGED, CTR><<<grid, H_THREADS, smem, st>>>(map, a);
   return check_launch("irr_conv2d_fwd");
@@ -1103,15 +1110,8 @@ static int launch_h16(const CUtensorMap& map, const HArgs& a, size_t smem, cudaS
 
 template <int NG, bool CTR>
 static int launch_roll(const CUtensorMap& map, const RArgs& r, size_t smem, int grid, cudaStream_t st) {
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_roll_kernel<NG, CTR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("irr_conv2d_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_smem = smem;
-  }
+  static SmemAttrCache attr = {};
+  if (int rc = ensure_dyn_smem(conv_roll_kernel<NG, CTR>, smem, attr, "irr_conv2d_fwd")) return rc;
   conv_roll_kernel<NG, CTR><<<grid, R_THREADS, smem, st>>>(map, r);
   return check_launch("irr_conv2d_fwd");
 }
@@ -1227,7 +1227,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr == CUDA_SUCCESS) {
-      const size_t rsmem = 9 * g.img_bytes + (size_t)R_XS * R_XBYTES + 40 * 8 + 64 * 4 + 64;
+      const size_t rsmem = 9 * g.img_bytes + (size_t)R_XS * R_XBYTES + 40 * 8 + 64 * 4 + 8 * 8 + 64;
       const int grid = r.items < sm_count() ? r.items : sm_count();
       const bool dbg = h_ctr_host != nullptr;
       int rc;

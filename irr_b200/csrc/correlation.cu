@@ -832,15 +832,8 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
                        int C, int H, int W, int shift, float slope, cudaStream_t st) {
   constexpr int CORR_SMEM = FUSED ? CORR_SMEM_FUSED : CORR_SMEM_PLAIN;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(corr_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
-    if (e != cudaSuccess) {
-      set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_done = true;
-  }
+  static SmemAttrCache attr = {};
+  if (int rc = ensure_dyn_smem(corr_kernel<FUSED>, CORR_SMEM, attr, fn)) return rc;
   int vec_ok = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec_ok && (W % 8 == 0) && (((long long)H * W) % 8 == 0) && (out_bs % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0))
     vec_ok = 2;  // every 8-pixel strip of every output plane is 32-byte aligned
@@ -854,18 +847,11 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
   if (vec_in && !corr_no_tma()) {
     constexpr int TSMEM = FUSED ? CORR_SMEM_TMA_FUSED : CORR_SMEM_TMA_PLAIN;
-    static bool tattr_done = false;
+    static SmemAttrCache tattr = {};
     CUtensorMap m1, m2;
     if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC) &&
         make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC)) {
-      if (!tattr_done) {
-        cudaError_t e = cudaFuncSetAttribute(corr_tma_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM);
-        if (e != cudaSuccess) {
-          set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-          return (int)e;
-        }
-        tattr_done = true;
-      }
+      if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED>, TSMEM, tattr, fn)) return rc;
       const int ctr = corr_ctr_on() ? 1 : 0;
       if (ctr) {
         static const unsigned long long zeros[32] = {0};

@@ -73,6 +73,19 @@ def _v(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int]:
     return t.data_ptr(), bs
 
 
+def _p(t: torch.Tensor, name: str, like: Optional[torch.Tensor] = None, numel: Optional[int] = None) -> int:
+    """data_ptr of a dense fp32 CUDA tensor (weights, bias, linspace vectors, masks, packed images) after checking what
+    the kernels assume: CUDA, float32, contiguous, on the same device as ``like``, at least ``numel`` elements."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError(f"irr_b200: {name} must be a contiguous fp32 CUDA tensor "
+                           f"(got {getattr(t, 'dtype', type(t))}, {getattr(t, 'device', '?')})")
+    if like is not None and t.device != like.device:
+        raise RuntimeError(f"irr_b200: {name} is on {t.device}, expected {like.device}")
+    if numel is not None and t.numel() < numel:
+        raise RuntimeError(f"irr_b200: {name} has {t.numel()} elements, needs {numel}")
+    return t.data_ptr()
+
+
 _lin_cache = {}
 
 
@@ -115,8 +128,8 @@ def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: floa
     ly = host_linspace(H, f1.device) if lin_y is None else lin_y
     p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
     _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd, p1, s1, p2, s2, pf, sf,
-            lx.data_ptr(), ly.data_ptr(), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp, shift, slope,
-            _grid_mode, _stream())
+            _p(lx, "lin_x", f1, W), _p(ly, "lin_y", f1, H), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp,
+            shift, slope, _grid_mode, _stream())
     return out
 
 
@@ -130,23 +143,26 @@ def warp(x, flow, height_im: int, width_im: int, div_flow: float, out=None, minu
     ly = host_linspace(H, x.device) if lin_y is None else lin_y
     px, sx = _v(x, "x"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
     pm, sm = (_v(minuend, "minuend") if minuend is not None else (None, 0))
-    _launch("warp", (B, C, H, W), _lib.load().irr_warp_fwd, px, sx, pf, sf, lx.data_ptr(), ly.data_ptr(), pm, sm, po, so,
-            mask_out.data_ptr() if mask_out is not None else None, B, C, H, W, height_im, width_im, div_flow, shift,
-            _grid_mode, _stream())
+    _launch("warp", (B, C, H, W), _lib.load().irr_warp_fwd, px, sx, pf, sf, _p(lx, "lin_x", x, W), _p(ly, "lin_y", x, H),
+            pm, sm, po, so, _p(mask_out, "mask_out", x, B * H * W) if mask_out is not None else None, B, C, H, W,
+            height_im, width_im, div_flow, shift, _grid_mode, _stream())
     return out
 
 
 def correlation_generic(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
     import ctypes
     B, C, H, W = in1.shape
+    if tuple(in2.shape) != tuple(in1.shape):
+        raise RuntimeError(f"irr_b200: correlation inputs differ in shape ({tuple(in1.shape)} vs {tuple(in2.shape)})")
     in1 = in1.contiguous(); in2 = in2.contiguous()
+    p1, p2 = _p(in1, "input1"), _p(in2, "input2", in1)
     oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     lib = _lib.load()
     _lib.check(lib.irr_correlation_generic_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
                                                      ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)),
                "correlation_generic_out_shape")
     out = torch.empty((B, oc.value, oh.value, ow.value), dtype=torch.float32, device=in1.device)
-    _launch("correlation_generic", (B, C, H, W), lib.irr_correlation_generic_fwd, in1.data_ptr(), in2.data_ptr(),
+    _launch("correlation_generic", (B, C, H, W), lib.irr_correlation_generic_fwd, p1, p2,
             out.data_ptr(), B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2, _stream())
     return out
 
@@ -169,7 +185,7 @@ def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
         raise RuntimeError(f"irr_b200: no packed layout for conv {Cout}x{Cin}x{ks} math={math}")
     packed = torch.empty(n // 4, dtype=torch.float32, device=w.device)
     wc = w.detach().contiguous().float()
-    _launch("conv2d_pack_weights", (Cout, Cin, ks), lib.irr_conv2d_pack_weights, wc.data_ptr(), packed.data_ptr(), Cout,
+    _launch("conv2d_pack_weights", (Cout, Cin, ks), lib.irr_conv2d_pack_weights, _p(wc, "weight"), packed.data_ptr(), Cout,
             Cin, ks, math, _stream())
     return packed
 
@@ -197,7 +213,7 @@ def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, s
         _ws_bytes[key] = nws
     ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
     _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_ws, px, sx,
-            packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, math,
+            _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, math,
             ws.data_ptr() if ws is not None else None, nws, _stream())
     return out
 
@@ -221,7 +237,7 @@ def conv2d_dual(x, packed, bias, Cout: int, n_split: int, ks: int, out, out2, st
         _ws_bytes[key] = nws
     ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
     _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_dual, px, sx,
-            packed.data_ptr(), bias.data_ptr(), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, n_split,
+            _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, n_split,
             pa2, sa2, po2, so2, slope2, alpha2, math, ws.data_ptr() if ws is not None else None, nws, _stream())
     return out, out2
 

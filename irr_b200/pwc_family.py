@@ -91,18 +91,13 @@ class PWCFamily(nn.Module):
             flow = occ = None
             for l, feat in enumerate(pyramid[:self.output_level + 1]):
                 _, C, h, w = feat.shape
-                x = feat if self.BI else feat[:B]          # the feature each row's estimator sees (x1 | x2)
-                last = l == self.output_level
                 if l == 0:
                     flow_up = torch.zeros((NB, 2, h, w), dtype=torch.float32, device=dev)
                     occ_up = torch.zeros((NB, 1, h, w), dtype=torch.float32, device=dev) if self.OCC else None
                 else:
                     flow_up = ops.resize_ac(flow, h, w)
                     occ_up = ops.resize_ac(occ, h, w) if self.OCC else None
-                if self.IRR:
-                    flow, occ = self._level_irr(l, feat, x, B, NB, flow_up, occ_up, height_im, width_im)
-                else:
-                    flow, occ = self._level_plain(l, feat, x, B, NB, C, flow_up, occ_up, last, height_im, width_im)
+                flow, occ = self.estimator_level(l, feat, flow_up, occ_up, height_im, width_im)
                 if record is not None:
                     record[l] = {"flow": flow.clone()}
                     if self.OCC:
@@ -111,6 +106,23 @@ class PWCFamily(nn.Module):
             if self.OCC:
                 out['occ'] = ops.resize_ac(occ[:B], height_im, width_im)
         return out
+
+    def estimator_level(self, l, feat, flow_up, occ_up, height_im, width_im):
+        """One pyramid level (the loop bodies cited above) given the level's inputs — the stage entry point the
+        teacher-forced parity tests drive.
+
+        feat   : (2B, C_l, h, w) rows [0,B) = x1 features, rows [B,2B) = x2 features
+        flow_up: (NB, 2, h, w) previous flow resized to this level (zeros at l == 0); NB = 2B for the *_bi classes
+                 (rows [0,B) forward, [B,2B) backward), else B
+        occ_up : (NB, 1, h, w) or None (classes without the occlusion branch)
+        returns (flow, occ-or-None) of this level."""
+        B = feat.shape[0] // 2
+        NB = 2 * B if self.BI else B
+        C = feat.shape[1]
+        x = feat if self.BI else feat[:B]          # the feature each row's estimator sees (x1 | x2)
+        if self.IRR:
+            return self._level_irr(l, feat, x, B, NB, flow_up, occ_up, height_im, width_im)
+        return self._level_plain(l, feat, x, B, NB, C, flow_up, occ_up, l == self.output_level, height_im, width_im)
 
     # pwcnet_irr.py:73-84, pwcnet_irr_bi.py:79-98, pwcnet_irr_occ.py:79-97
     def _level_irr(self, l, feat, x, B, NB, flow_up, occ_up, height_im, width_im):

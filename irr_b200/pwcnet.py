@@ -37,6 +37,40 @@ class PWCNet(nn.Module):
                             "stride1": 1, "stride2": 1, "corr_multiply": 1}
         initialize_msra(self.modules())
 
+    def estimator_level(self, l, feat, flow_up, height_im, width_im, record=None):
+        """One pass of pwcnet.py:62-92 for pyramid level l on the stacked pair.
+
+        feat   : (2B, C_l, h, w) rows [0,B) = x1 features, rows [B,2B) = x2 features
+        flow_up: (B, 2, h, w) the previous level's flow already resized to this level (ignored at l == 0)
+        returns this level's flow (B, 2, h, w) — after the context network at the output level."""
+        B = feat.shape[0] // 2
+        df = self._div_flow
+        x1, x2 = feat[:B], feat[B:]
+        _, C, h, w = x1.shape
+        est = self.flow_estimators[l]
+        last = l == self.output_level
+        buf = torch.empty((B, est.total_ch + (2 if last else 0), h, w), dtype=torch.float32, device=feat.device)
+        corr = buf[:, 448:529]
+        if l == 0:  # pwcnet.py:66-68,73-74
+            ops.correlation(x1, x2, out=corr, slope=0.1)
+        else:       # pwcnet.py:69-74
+            ops.warp_correlation(x1, x2, flow_up, height_im, width_im, df, out=corr, slope=0.1)
+            ops.scale_channels(x1, out=buf[:, 529:529 + C])          # pwcnet.py:80 cat[corr, x1, flow]
+            ops.scale_channels(flow_up, out=buf[:, 529 + C:531 + C])
+        if record is not None:
+            record["corr"] = corr.clone()
+        if not last:
+            flow = est.forward_into(buf)
+        else:  # pwcnet.py:85-88: flow + context(cat[x_intm, flow])
+            tail = buf[:, est.total_ch:est.total_ch + 2]
+            est.forward_into(buf, out=tail)
+            if record is not None:
+                record["flow_est"] = tail.clone()
+            flow = self.context_networks(buf, addend=tail)
+        if record is not None:
+            record["flow"] = flow.clone()
+        return flow
+
     def forward(self, input_dict, record=None):
         if self.training:
             raise RuntimeError("irr_b200.pwcnet: only the eval-mode forward is implemented (call .eval())")
@@ -48,28 +82,12 @@ class PWCNet(nn.Module):
             pyramid = self.feature_pyramid_extractor(imgs)
             flow = None
             for l, feat in enumerate(pyramid[:self.output_level + 1]):
-                x1, x2 = feat[:B], feat[B:]
-                _, C, h, w = x1.shape
-                est = self.flow_estimators[l]
-                last = l == self.output_level
-                buf = torch.empty((B, est.total_ch + (2 if last else 0), h, w), dtype=torch.float32, device=imgs.device)
-                corr = buf[:, 448:529]
-                if l == 0:  # pwcnet.py:66-68,73-74
-                    ops.correlation(x1, x2, out=corr, slope=0.1)
-                else:       # pwcnet.py:69-74
+                _, _, h, w = feat.shape
+                if l > 0:
                     flow = ops.resize_ac(flow, h, w)
-                    ops.warp_correlation(x1, x2, flow, height_im, width_im, df, out=corr, slope=0.1)
-                    ops.scale_channels(x1, out=buf[:, 529:529 + C])          # pwcnet.py:80 cat[corr, x1, flow]
-                    ops.scale_channels(flow, out=buf[:, 529 + C:531 + C])
+                rec_l = None
                 if record is not None:
-                    record[l] = {"corr": corr.clone()}
-                if not last:
-                    flow = est.forward_into(buf)
-                else:  # pwcnet.py:85-88: flow + context(cat[x_intm, flow])
-                    tail = buf[:, est.total_ch:est.total_ch + 2]
-                    est.forward_into(buf, out=tail)
-                    flow = self.context_networks(buf, addend=tail)
-                if record is not None:
-                    record[l]["flow"] = flow.clone()
+                    rec_l = record[l] = {}
+                flow = self.estimator_level(l, feat, flow, height_im, width_im, rec_l)
             out = ops.resize_ac(flow, height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df)  # pwcnet.py:97
         return {'flow': out}

@@ -41,6 +41,43 @@ class PWCNet(nn.Module):
                             "stride1": 1, "stride2": 1, "corr_multiply": 1}
         initialize_msra(self.modules())
 
+    def estimator_level(self, l, feat, flow_up, occ_up, height_im, width_im, record=None):
+        """One pass of pwcnet_irr_occ_bi.py:66-121 for pyramid level l on the 2B batch.
+
+        feat   : (2B, C_l, h, w) rows [0,B) = x1 features, rows [B,2B) = x2 features
+        flow_up: (2B, 2, h, w) flow in GLOBAL units already resized to this level (zeros at l == 0); rows [0,B) forward
+        occ_up : (2B, 1, h, w)
+        returns (flow in GLOBAL units, occ) of this level on the 2B batch."""
+        B2, C, h, w = feat.shape
+        B = B2 // 2
+        dev = feat.device
+        df = self._div_flow
+        nf, no = self.num_ch_in_flo, self.num_ch_in_occ
+        buf_f = torch.empty((B2, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
+        buf_o = torch.empty((B2, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
+        corr = buf_f[:, 448:529]
+        if l == 0:  # pwcnet_irr_occ_bi.py:68-70,82-85
+            ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
+        else:       # :72-85
+            ops.warp_correlation(feat, feat, flow_up, height_im, width_im, df, out=corr, shift=B, slope=0.1)
+        self.conv_1x1[l](feat, out=buf_f[:, 529:561])  # :91-92
+        ops.scale_channels(buf_f[:, 448:561], out=buf_o[:, 448:561])
+        su_l, sv_l = flow_scales(h, w, df, width_im, height_im, True)
+        su_g, sv_g = flow_scales(h, w, df, width_im, height_im, False)
+        ops.scale_channels(flow_up, out=buf_f[:, 561:563], s_even=su_l, s_odd=sv_l)  # :88-89
+        ops.scale_channels(occ_up, out=buf_o[:, 561:562])
+        # flow (:93-104)
+        self.flow_estimators.forward_into(buf_f, out=buf_f[:, 563:565], addend=buf_f[:, 561:563])
+        flow = self.context_networks(buf_f, addend=buf_f[:, 563:565])
+        ops.scale_channels(flow, out=flow, s_even=su_g, s_odd=sv_g)
+        # occlusion (:109-117)
+        self.occ_estimators.forward_into(buf_o, out=buf_o[:, 562:563], addend=buf_o[:, 561:562])
+        occ = self.occ_context_networks(buf_o, addend=buf_o[:, 562:563])
+        if record is not None:
+            record.update({"corr": corr.clone(), "x_1by1": buf_f[:, 529:561].clone(), "flow": flow.clone(),
+                           "occ": occ.clone(), "flow_up": flow_up.clone(), "occ_up": occ_up.clone()})
+        return flow, occ
+
     def forward(self, input_dict, record=None):
         if self.training:
             raise RuntimeError("irr_b200.pwcnet_irr_occ_bi: only the eval-mode forward is implemented (call .eval())")
@@ -48,7 +85,6 @@ class PWCNet(nn.Module):
         B, _, height_im, width_im = x1_raw.shape
         B2 = 2 * B
         df = self._div_flow
-        nf, no = self.num_ch_in_flo, self.num_ch_in_occ
         with torch.no_grad():
             imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()
             dev = imgs.device
@@ -56,33 +92,16 @@ class PWCNet(nn.Module):
             flow = occ = None
             for l, feat in enumerate(pyramid[:self.output_level + 1]):
                 _, C, h, w = feat.shape
-                buf_f = torch.empty((B2, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
-                buf_o = torch.empty((B2, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
-                corr = buf_f[:, 448:529]
-                if l == 0:  # pwcnet_irr_occ_bi.py:68-70,82-85
+                if l == 0:
                     flow_up = torch.zeros((B2, 2, h, w), dtype=torch.float32, device=dev)
                     occ_up = torch.zeros((B2, 1, h, w), dtype=torch.float32, device=dev)
-                    ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
-                else:       # :72-85
+                else:
                     flow_up = ops.resize_ac(flow, h, w)
                     occ_up = ops.resize_ac(occ, h, w)
-                    ops.warp_correlation(feat, feat, flow_up, height_im, width_im, df, out=corr, shift=B, slope=0.1)
-                self.conv_1x1[l](feat, out=buf_f[:, 529:561])  # :91-92
-                ops.scale_channels(buf_f[:, 448:561], out=buf_o[:, 448:561])
-                su_l, sv_l = flow_scales(h, w, df, width_im, height_im, True)
-                su_g, sv_g = flow_scales(h, w, df, width_im, height_im, False)
-                ops.scale_channels(flow_up, out=buf_f[:, 561:563], s_even=su_l, s_odd=sv_l)  # :88-89
-                ops.scale_channels(occ_up, out=buf_o[:, 561:562])
-                # flow (:93-104)
-                self.flow_estimators.forward_into(buf_f, out=buf_f[:, 563:565], addend=buf_f[:, 561:563])
-                flow = self.context_networks(buf_f, addend=buf_f[:, 563:565])
-                ops.scale_channels(flow, out=flow, s_even=su_g, s_odd=sv_g)
-                # occlusion (:109-117)
-                self.occ_estimators.forward_into(buf_o, out=buf_o[:, 562:563], addend=buf_o[:, 561:562])
-                occ = self.occ_context_networks(buf_o, addend=buf_o[:, 562:563])
+                rec_l = None
                 if record is not None:
-                    record[l] = {"corr": corr.clone(), "flow": flow.clone(), "occ": occ.clone(),
-                                 "flow_up": flow_up.clone(), "occ_up": occ_up.clone()}
+                    rec_l = record[l] = {}
+                flow, occ = self.estimator_level(l, feat, flow_up, occ_up, height_im, width_im, rec_l)
             out_flow = ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df)  # :130
             out_occ = ops.resize_ac(occ[:B], height_im, width_im)  # :131
         return {'flow': out_flow, 'occ': out_occ}

@@ -382,6 +382,9 @@ def pwc_family_forward(model: str, p: Params, img1, img2, div_flow=0.05, record:
                 occ_f = resize_ac(occ_f, x1)
                 if bi:
                     occ_b = resize_ac(occ_b, x2)
+        rec(f"l{l}.x1", x1); rec(f"l{l}.x2", x2)
+        rec(f"l{l}.flow_up_f", flow_f); rec(f"l{l}.flow_up_b", flow_b)
+        rec(f"l{l}.occ_up_f", occ_f); rec(f"l{l}.occ_up_b", occ_b)
         corr_f = F.leaky_relu(cost_volume(x1, x2w), LEAKY)
         corr_b = F.leaky_relu(cost_volume(x2, x1w), LEAKY) if bi else None
         rec(f"l{l}.corr_f", corr_f)
@@ -431,6 +434,8 @@ def pwc_family_forward(model: str, p: Params, img1, img2, div_flow=0.05, record:
             rec(f"l{l}.flow_b", flow_b)
         if occ:
             rec(f"l{l}.occ_f", occ_f)
+            if bi:
+                rec(f"l{l}.occ_b", occ_b)
         if l == OUT_LEVEL:
             break
     out = {"flow": resize_ac(flow_f, img1) * (1.0 / div_flow)}

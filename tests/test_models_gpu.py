@@ -262,22 +262,78 @@ def test_family_models_end_to_end(cuda, golden_dir, conv_math, name):
             assert O.epe(got["flow"].cpu(), gold).item() <= 2e-2 * scale
 
 
-def test_other_models_teacher_forced(cuda):
-    """Per-level record comparison for PWCNet_irr_occ_bi and PWCNet: level-l outputs given bit-close level inputs.
-    Level 0 and 1 have no upstream mask chaos, so they are compared at 1e-4 directly."""
-    for name in ("PWCNet", "PWCNet_irr_occ_bi"):
-        m, p = build(name, cuda)
-        i1, i2, _ = O.synthetic_pair(1, 128, 192, seed=9, max_flow=4.0)
-        rec, mine = {}, {}
+_ORACLE_RUNS = {}
+
+
+def _oracle_levels(name, H, W):
+    """The oracle's per-level inputs and outputs for one (class, size); cached across conv-math parametrisations."""
+    key = (name, H, W)
+    if key not in _ORACLE_RUNS:
+        p = O.synthetic_params(name, seed=1234, gain=0.7)
+        i1, i2, _ = O.synthetic_pair(1, H, W, seed=9, max_flow=4.0)
+        rec = {}
         with torch.no_grad():
-            O.FORWARDS[name](p, i1, i2, record=rec)
-            m({"input1": i1.to(cuda), "input2": i2.to(cuda)}, record=mine)
+            out = O.FORWARDS[name](p, i1, i2, record=rec)
+        _ORACLE_RUNS[key] = (p, i1, i2, rec, out)
+    return _ORACLE_RUNS[key]
+
+
+ALL_BUT_IRR_PWC = ["PWCNet", "PWCNet_irr_occ_bi"] + sorted(O.FAMILY)
+
+
+@pytest.mark.parametrize("hw", [(128, 192), (94, 156)])
+@pytest.mark.parametrize("name", ALL_BUT_IRR_PWC)
+def test_pwc_classes_every_level_teacher_forced(cuda, conv_math, name, hw):
+    """VERDICT r1 'next' #1: every pyramid level l = 0..4 of the eight classes that are not IRR_PWC, fed the ORACLE's
+    level inputs (features, up-sampled flow / occlusion), must reproduce the oracle's level outputs to 1e-4 — so a real
+    discrepancy in a level body cannot hide behind the mask chaos of the end-to-end comparison."""
+    import irr_b200
+    H, W = hw
+    p, i1, i2, rec, _ = _oracle_levels(name, H, W)
+    m = irr_b200.MODELS[name](None)
+    irr_b200.load_state_dict_strict(m, p)
+    m = m.to(cuda).eval()
+    irr, bi, occ = {"PWCNet": (False, False, False), "PWCNet_irr_occ_bi": (True, True, True)}.get(name) or O.FAMILY[name]
+    worst = {}
+
+    def both(key, l):  # (2B or B, ...) tensor in the layout of the CUDA path
         if name == "PWCNet":
-            assert maxdiff(mine[0]["corr"], rec["l0.corr"]) <= TOL
-            assert maxdiff(mine[0]["flow"], rec["l0.flow"]) <= TOL
-        else:
-            assert maxdiff(mine[0]["flow"], torch.cat([rec["l0.flow_f"], rec["l0.flow_b"]], 0)) <= TOL
-            assert maxdiff(mine[0]["occ"], torch.cat([rec["l0.occ_f"], rec["l0.occ_b"]], 0)) <= TOL
+            return rec[f"l{l}.{key}"].to(cuda).contiguous()
+        if bi:
+            return torch.cat([rec[f"l{l}.{key}_f"], rec[f"l{l}.{key}_b"]], 0).to(cuda).contiguous()
+        return rec[f"l{l}.{key}_f"].to(cuda).contiguous()
+
+    def check(what, got, ref):
+        d = maxdiff(got, ref)
+        tol = TOL * max(1.0, ref.abs().max().item())
+        worst[what] = max(worst.get(what, 0.0), d / max(1.0, ref.abs().max().item()))
+        assert d <= tol, f"{name} {H}x{W} level {what}: max-abs {d:.3e} > {tol:.3e}"
+
+    with torch.no_grad():
+        for l in range(5):
+            feat = torch.cat([rec[f"l{l}.x1"], rec[f"l{l}.x2"]], 0).to(cuda).contiguous()
+            flow_up = both("flow_up", l)
+            if name == "PWCNet":
+                mine = {}
+                flow = m.estimator_level(l, feat, flow_up, H, W, record=mine)
+                check(f"l{l}.corr", mine["corr"], rec[f"l{l}.corr"])
+                check(f"l{l}.flow", flow, rec[f"l{l}.flow"])
+                continue
+            occ_up = both("occ_up", l) if occ else None
+            flow, occ_out = m.estimator_level(l, feat, flow_up, occ_up, H, W)
+            check(f"l{l}.flow", flow, both("flow", l))
+            if occ:
+                check(f"l{l}.occ", occ_out, both("occ", l))
+    _note(f"[teacher-forced] {name} {H}x{W} math={conv_math}: worst scaled max-abs per stage "
+          + ", ".join(f"{k}={v:.1e}" for k, v in worst.items()))
+
+
+def _note(msg):
+    import os
+    print(msg)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.txt", "a") as f:
+        f.write(msg + "\n")
 
 
 def test_module_api_matches_reference_modules(cuda, golden_dir):
