@@ -133,6 +133,30 @@ int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, co
                         long long addend2_bs, float* y2, long long y2_bs, float leaky_slope2, float alpha2, int math,
                         void* workspace, size_t workspace_bytes, irr_stream_t stream);
 
+/* The general form of the two above (IRR_MATH_TC_3XF16 only): the output channels are cut into up to IRR_CONV_MAX_SEGS
+ * consecutive segments, segment i = channels [n_begin_i, n_begin_{i+1}) (n_begin_0 = 0, every n_begin a multiple of 16),
+ * each with its own destination slice and epilogue
+ *     y_i = addend_i + alpha_i * act_i(conv + bias)                  (addend_pre == 0)
+ *     y_i = alpha_i * act_i(conv + bias + addend_i)                  (addend_pre != 0: a partial sum of the SAME layer
+ *                                                                     computed by an earlier pass over other input channels)
+ * This is how the dense estimators (models/pwc_modules.py:153-170) run conv4, the part of conv5 and the part of
+ * conv_last that read conv4's input as ONE pass: the thin layers' partial sums ride along as extra output columns of a
+ * layer whose activations are being staged anyway.  `segs` is a host array read during the call. */
+#define IRR_CONV_MAX_SEGS 4
+typedef struct irr_conv_seg {
+  int n_begin;          /* first output channel of the segment */
+  int addend_pre;       /* 0: addend is added after the activation; 1: before it */
+  float leaky_slope;    /* 1.0f = no activation */
+  float alpha;
+  const float* addend;  /* B x n_i x Ho x Wo slice or NULL */
+  long long addend_bs;
+  float* y;             /* destination slice: channel n of the layer goes to y[:, n - n_begin] */
+  long long y_bs;
+} irr_conv_seg;
+int irr_conv2d_fwd_multi(const float* x, long long x_bs, const void* w_packed, const float* bias, int B, int Cin, int H,
+                         int W, int Cout, int ksize, int stride, int dilation, const irr_conv_seg* segs, int n_segs, int math,
+                         void* workspace, size_t workspace_bytes, irr_stream_t stream);
+
 /* A8 — upsample2d_as (models/pwc_modules.py:65-67): bilinear, align_corners=True, any in/out size, fused with an
  * optional per-channel-parity scale (even channels * scale_even, odd * scale_odd): rescale_flow of
  * pwc_modules.py:70-82 applied to the resized flow, or the final *(1/div_flow) of IRR_PWC.py:176. */

@@ -12,6 +12,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libirr_b200.so")
 
 c_fp = C.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
+
+
+class ConvSeg(C.Structure):
+    """``irr_conv_seg`` of include/irr_b200.h (one output-channel segment of irr_conv2d_fwd_multi)."""
+    _fields_ = [("n_begin", C.c_int), ("addend_pre", C.c_int), ("leaky_slope", C.c_float), ("alpha", C.c_float),
+                ("addend", C.c_void_p), ("addend_bs", C.c_longlong), ("y", C.c_void_p), ("y_bs", C.c_longlong)]
+
+
 c_ll = C.c_longlong
 c_i = C.c_int
 c_f = C.c_float
@@ -40,6 +48,8 @@ PROTOTYPES = {
                           c_f, c_i, c_fp, C.c_size_t, c_fp],
     "irr_conv2d_fwd_dual": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                             c_f, c_i, c_fp, c_ll, c_fp, c_ll, c_f, c_f, c_i, c_fp, C.c_size_t, c_fp],
+    "irr_conv2d_fwd_multi": [c_fp, c_ll, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, C.POINTER(ConvSeg), c_i, c_i, c_fp,
+                             C.c_size_t, c_fp],
     "irr_resize_bilinear_ac_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_fp],
     "irr_scale_channels_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_f, c_f, c_fp],
     "irr_round_bf16_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],

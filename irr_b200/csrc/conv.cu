@@ -16,15 +16,14 @@ int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, co
 bool tc_supported(int Cout, int Cin, int ks, int stride, int dil);
 size_t h16_packed_bytes(int Cout, int Cin, int ks);
 int h16_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st);
-struct H16Dual {
-  int n_split;
-  float* y2; long long y2_bs;
-  const float* addend2; long long a2_bs;
-  float slope2, alpha2;
+struct HSeg {  // must match conv_tc16.cu
+  int n_begin, pre;
+  float slope, alpha;
+  const float* addend; long long a_bs;
+  float* y; long long y_bs;
 };
-int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
-             float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
-             float alpha, const H16Dual* dual, void* ws, size_t ws_bytes, cudaStream_t st);
+int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const HSeg* segs, int nseg, int B, int Cin,
+             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil);
 }  // namespace irr
 
@@ -105,8 +104,9 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
       set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);
       return IRR_E_UNSUPPORTED;
     }
-    return h16_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
-                    leaky_slope, alpha, nullptr, workspace, workspace_bytes, as_stream(stream));
+    HSeg sg = {0, 0, leaky_slope, alpha, addend, addend_bs, y, y_bs};
+    return h16_conv(x, x_bs, w_packed, bias, &sg, 1, B, Cin, H, W, Cout, ksize, stride, dilation, workspace, workspace_bytes,
+                    as_stream(stream));
   }
   return fail_arg(fn, "unknown math mode");
 }
@@ -128,10 +128,36 @@ int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, co
     set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);
     return IRR_E_UNSUPPORTED;
   }
-  H16Dual d;
-  d.n_split = n_split; d.y2 = y2; d.y2_bs = y2_bs; d.addend2 = addend2; d.a2_bs = addend2_bs; d.slope2 = leaky_slope2; d.alpha2 = alpha2;
-  return h16_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
-                  leaky_slope, alpha, &d, workspace, workspace_bytes, as_stream(stream));
+  HSeg sg[2] = {{0, 0, leaky_slope, alpha, addend, addend_bs, y, y_bs},
+                {n_split, 0, leaky_slope2, alpha2, addend2, addend2_bs, y2, y2_bs}};
+  return h16_conv(x, x_bs, w_packed, bias, sg, 2, B, Cin, H, W, Cout, ksize, stride, dilation, workspace, workspace_bytes,
+                  as_stream(stream));
+}
+
+int irr_conv2d_fwd_multi(const float* x, long long x_bs, const void* w_packed, const float* bias, int B, int Cin, int H,
+                         int W, int Cout, int ksize, int stride, int dilation, const irr_conv_seg* segs, int n_segs, int math,
+                         void* workspace, size_t workspace_bytes, irr_stream_t stream) {
+  const char* fn = "irr_conv2d_fwd_multi";
+  IRR_REQUIRE(x && w_packed && bias && segs, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
+  IRR_REQUIRE(ksize == 1 || ksize == 3, fn, "kernel_size must be 1 or 3");
+  IRR_REQUIRE(stride >= 1 && dilation >= 1, fn, "stride/dilation must be >= 1");
+  IRR_REQUIRE(math == IRR_MATH_TC_3XF16, fn, "output segments are implemented by the IRR_MATH_TC_3XF16 path only");
+  IRR_REQUIRE(n_segs >= 1 && n_segs <= IRR_CONV_MAX_SEGS, fn, "n_segs must be in [1, IRR_CONV_MAX_SEGS]");
+  IRR_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, fn, "w_packed must be 16-byte aligned");
+  if (!tc_supported(Cout, Cin, ksize, stride, dilation)) {
+    set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);
+    return IRR_E_UNSUPPORTED;
+  }
+  HSeg sg[IRR_CONV_MAX_SEGS];
+  for (int i = 0; i < n_segs; ++i) {
+    IRR_REQUIRE(segs[i].y != nullptr, fn, "segment without a destination");
+    sg[i].n_begin = segs[i].n_begin; sg[i].pre = segs[i].addend_pre ? 1 : 0; sg[i].slope = segs[i].leaky_slope;
+    sg[i].alpha = segs[i].alpha; sg[i].addend = segs[i].addend; sg[i].a_bs = segs[i].addend_bs; sg[i].y = segs[i].y;
+    sg[i].y_bs = segs[i].y_bs;
+  }
+  return h16_conv(x, x_bs, w_packed, bias, sg, n_segs, B, Cin, H, W, Cout, ksize, stride, dilation, workspace,
+                  workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

@@ -50,29 +50,32 @@ constexpr int H_SB_MAX = 16;    // weight ring depth limit
 constexpr int H_HDR = 128;      // packed-weights header bytes: {float max_abs, float inv_scale, float scale}
 constexpr size_t H_SMEM_MAX = 225 * 1024;
 
+// Output-channel segment: channels [n_begin, next segment's n_begin) go to `y` (channel n - n_begin of that slice) with
+// their own epilogue  y = addend + alpha * act(acc + bias)   or, with `pre`,  y = alpha * act(acc + bias + addend).
+struct HSeg {
+  int n_begin, pre;
+  float slope, alpha;
+  const float* addend; long long a_bs;
+  float* y; long long y_bs;
+};
+constexpr int H_MAXSEG = 4;
+struct HSegs {
+  HSeg s[H_MAXSEG];
+  int n;
+};
+
 struct HArgs {
   const float* x; long long x_bs;
   const uint8_t* wp;
   const float* bias;
-  const float* addend; long long a_bs;
-  float* y; long long y_bs;
+  HSegs seg;
   int B, Cin, H, W, Cout, Ho, Wo, stride, dil, pad;
   int n_tile, n_tiles, cchunks, nkb, sb, resident;
   unsigned b_smem_bytes, x_stage_bytes;
   int rw_log2, rh, R, PW, padl, split, ytiles, xtiles, m_items, items;
   int ksplit, cps;            // split-K: K chunks are dealt to `ksplit` CTAs per tile, `cps` chunks each
   float* ws; long long ws_stride;  // split-K partial sums [ksplit][B][Cout][Ho*Wo] (raw accumulators)
-  // dual output: channels [n_split, Cout) go to y2 with their own epilogue (n_split % 16 == 0; == Cout when unused)
-  int n_split; float* y2; long long y2_bs; const float* addend2; long long a2_bs; float slope2, alpha2;
   long long M;
-  float slope1, alpha1;
-};
-
-struct H16Dual {  // second destination for output channels [n_split, Cout)
-  int n_split;
-  float* y2; long long y2_bs;
-  const float* addend2; long long a2_bs;
-  float slope2, alpha2;
 };
 
 struct HGeom {
@@ -572,25 +575,26 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
         }
         const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
-        const float* ap1 = (p.addend != nullptr && !raw) ? p.addend + (size_t)ob * p.a_bs + opix : nullptr;
-        const float* ap2 = (p.addend2 != nullptr && !raw) ? p.addend2 + (size_t)ob * p.a2_bs + opix : nullptr;
-        float* yp1 = raw ? p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix
-                         : p.y + (size_t)ob * p.y_bs + opix;
-        float* yp2 = raw ? yp1 : (p.y2 != nullptr ? p.y2 + (size_t)ob * p.y2_bs + opix : yp1);
+        float* ywr = p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix;  // raw split-K partials
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 16) {
           const int nb = nt * N + c0;
           const int nvalid = min(16, p.Cout - nb);  // warp-uniform; < 16 only in the layer's last channel group
           if (nvalid <= 0) break;
-          // dual output (fused conv5 + conv_last tail of the dense estimators): groups past n_split use the second
-          // destination, residual and activation; raw split-K partials keep the single [Cout] layout
-          const bool sec = !raw && nb >= p.n_split;
-          const int cb = sec ? nb - p.n_split : nb;
-          const float* ap = sec ? ap2 : ap1;
+          // output segments (fused tails of the dense estimators): each 16-channel group belongs to one segment with its
+          // own destination, residual and activation; raw split-K partials keep the single [Cout] layout
+          int si = 0;
+#pragma unroll
+          for (int k = 1; k < H_MAXSEG; ++k)
+            if (k < p.seg.n && nb >= p.seg.s[k].n_begin) si = k;
+          const HSeg& sg = p.seg.s[si];
+          const int cb = raw ? nb : nb - sg.n_begin;
+          const float* ap = (sg.addend != nullptr && !raw) ? sg.addend + (size_t)ob * sg.a_bs + opix : nullptr;
           const bool has_add = ap != nullptr;
-          float* yp = sec ? yp2 : yp1;
-          const float slope = sec ? p.slope2 : p.slope1;
-          const float alpha = sec ? p.alpha2 : p.alpha1;
+          const bool pre = sg.pre != 0;
+          float* yp = raw ? ywr : sg.y + (size_t)ob * sg.y_bs + opix;
+          const float slope = sg.slope;
+          const float alpha = sg.alpha;
           // residual / skip operand: 16 independent loads in flight before the accumulator is touched
           float add[16];
 #pragma unroll
@@ -610,8 +614,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           float val[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = fmaf(__uint_as_float(r[j]), inv_scale, bs[j]);
-            val[j] = raw ? __uint_as_float(r[j]) : fmaf(leaky(a, slope), alpha, add[j]);
+            float a = fmaf(__uint_as_float(r[j]), inv_scale, bs[j]);
+            if (pre) a += add[j];
+            val[j] = raw ? __uint_as_float(r[j]) : fmaf(leaky(a, slope), alpha, pre ? 0.f : add[j]);
           }
           if (m_ok) {
             if (nvalid == 16) {
@@ -932,6 +937,16 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < NG * 16; ++j) add[j] = 0.f;
         if (has_add) {
+          // Pull the residual rows of the next output rows into L2 (one 128-byte line per thread: channel t/4, 32-pixel
+          // segment t%4).  ncu (r01 capture): the epilogue warps spent half their time on the long-scoreboard stall of
+          // these loads, a DRAM round trip per output row with only one row's loads in flight.
+          if (oi + 2 < nr) {
+            const int pch = t >> 2, pxs = x0 + (t & 3) * 32;
+            if (pch < p.Cout && pxs < p.W) {
+              const float* pa = p.addend + (size_t)b * p.a_bs + (size_t)pch * HW + (size_t)(ya + oi + 2) * p.W + pxs;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            }
+          }
           const float* ap = p.addend + (size_t)b * p.a_bs + opix;
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
@@ -1005,10 +1020,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------ split-K finish
 // y = addend + alpha * act(inv_scale * sum_s ws[s] + bias): the partial sums are added in split order (deterministic).
 __global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_stride, int S, const uint8_t* __restrict__ wp,
-                                  const float* __restrict__ bias, const float* __restrict__ addend, long long a_bs,
-                                  float* __restrict__ y, long long y_bs, int Cout, int HWo, long long total, float slope,
-                                  float alpha, int n_split, const float* __restrict__ addend2, long long a2_bs,
-                                  float* __restrict__ y2, long long y2_bs, float slope2, float alpha2) {
+                                  const float* __restrict__ bias, HSegs seg, int Cout, int HWo, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float inv_scale = __ldg(reinterpret_cast<const float*>(wp) + 1);
@@ -1018,16 +1030,16 @@ __global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_str
   const long long b = r / Cout;
   float acc = 0.f;
   for (int s = 0; s < S; ++s) acc += __ldg(ws + (size_t)s * ws_stride + i);
-  const float a = fmaf(acc, inv_scale, __ldg(bias + c));
-  if (c < n_split) {
-    const size_t o = (size_t)c * HWo + pix;
-    const float add = addend ? __ldg(addend + (size_t)b * a_bs + o) : 0.f;
-    y[(size_t)b * y_bs + o] = fmaf(leaky(a, slope), alpha, add);
-  } else {
-    const size_t o = (size_t)(c - n_split) * HWo + pix;
-    const float add = addend2 ? __ldg(addend2 + (size_t)b * a2_bs + o) : 0.f;
-    y2[(size_t)b * y2_bs + o] = fmaf(leaky(a, slope2), alpha2, add);
-  }
+  float a = fmaf(acc, inv_scale, __ldg(bias + c));
+  int si = 0;
+#pragma unroll
+  for (int k = 1; k < H_MAXSEG; ++k)
+    if (k < seg.n && c >= seg.s[k].n_begin) si = k;
+  const HSeg& sg = seg.s[si];
+  const size_t o = (size_t)(c - sg.n_begin) * HWo + pix;
+  const float add = sg.addend ? __ldg(sg.addend + (size_t)b * sg.a_bs + o) : 0.f;
+  if (sg.pre) a += add;
+  sg.y[(size_t)b * sg.y_bs + o] = fmaf(leaky(a, sg.slope), sg.alpha, sg.pre ? 0.f : add);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packer
@@ -1179,25 +1191,29 @@ size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int s
   return k > 1 ? (size_t)k * B * Cout * Ho * Wo * sizeof(float) : 0;
 }
 
-int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
-             float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil, float slope,
-             float alpha, const H16Dual* dual, void* ws, size_t ws_bytes, cudaStream_t st) {
+int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const HSeg* segs, int nseg, int B, int Cin,
+             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st) {
   HGeom g = h_geom(Cout, Cin, ks);
   HArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.x_bs = x_bs; a.wp = (const uint8_t*)w; a.bias = bias; a.addend = addend; a.a_bs = a_bs; a.y = y; a.y_bs = y_bs;
+  if (nseg < 1 || nseg > H_MAXSEG || segs[0].n_begin != 0) return fail_arg("irr_conv2d_fwd", "bad output segments");
+  for (int i = 0; i < nseg; ++i) {
+    if (segs[i].y == nullptr || (segs[i].n_begin % 16) != 0 || segs[i].n_begin >= Cout || (i > 0 && segs[i].n_begin <= segs[i - 1].n_begin))
+      return fail_arg("irr_conv2d_fwd", "output segments must start at increasing multiples of 16 below Cout");
+    a.seg.s[i] = segs[i];
+  }
+  a.seg.n = nseg;
+  const float* addend = segs[0].addend; const long long a_bs = segs[0].a_bs;
+  float* y = segs[0].y; const long long y_bs = segs[0].y_bs;
+  const float slope = segs[0].slope, alpha = segs[0].alpha;
+  const bool single = nseg == 1 && segs[0].pre == 0;   // the plain layer: what the rolling kernel implements
+  a.x = x; a.x_bs = x_bs; a.wp = (const uint8_t*)w; a.bias = bias;
   a.B = B; a.Cin = Cin; a.H = H; a.W = W; a.Cout = Cout; a.stride = stride; a.dil = dil;
   a.pad = ((ks - 1) * dil) / 2;
   a.Ho = (H + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
   a.Wo = (W + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
   a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb;
   a.M = (long long)B * a.Ho * a.Wo;
-  a.slope1 = slope; a.alpha1 = alpha;
-  a.n_split = Cout; a.y2 = nullptr; a.y2_bs = 0; a.addend2 = nullptr; a.a2_bs = 0; a.slope2 = 1.f; a.alpha2 = 1.f;
-  if (dual != nullptr && dual->n_split > 0 && dual->n_split < Cout) {
-    a.n_split = dual->n_split; a.y2 = dual->y2; a.y2_bs = dual->y2_bs; a.addend2 = dual->addend2; a.a2_bs = dual->a2_bs;
-    a.slope2 = dual->slope2; a.alpha2 = dual->alpha2;
-  }
   const size_t misc = 56 * 8 + 256 * 4 + 64;
   const size_t total_b = (size_t)g.nkb * g.img_bytes;
 
@@ -1207,7 +1223,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   // ---- rolling kernel: single-chunk thin layers on wide images
-  if (tma_ok && !no_roll() && dual == nullptr && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
+  if (tma_ok && !no_roll() && single && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
     RArgs r;
     memset(&r, 0, sizeof(r));
     r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
@@ -1306,10 +1322,8 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   else rc = ks == 1 ? launch_h16<1, false>(map, a, smem, st) : launch_h16<3, false>(map, a, smem, st);
   if (rc != 0 || a.ksplit == 1) return rc;
   const long long total = (long long)B * Cout * a.Ho * a.Wo;
-  h16_splitk_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.ws, a.ws_stride, a.ksplit, a.wp, bias, addend, a_bs, y,
-                                                                     y_bs, Cout, a.Ho * a.Wo, total, slope, alpha,
-                                                                     a.n_split, a.addend2, a.a2_bs, a.y2 ? a.y2 : y, a.y2_bs,
-                                                                     a.slope2, a.alpha2);
+  h16_splitk_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.ws, a.ws_stride, a.ksplit, a.wp, bias, a.seg, Cout,
+                                                                     a.Ho * a.Wo, total);
   return check_launch("irr_conv2d_fwd");
 }
 

@@ -242,6 +242,40 @@ def conv2d_dual(x, packed, bias, Cout: int, n_split: int, ks: int, out, out2, st
     return out, out2
 
 
+def conv2d_multi(x, packed, bias, Cout: int, ks: int, segs, stride: int = 1, dil: int = 1, math: int = MATH_TC_3XF16):
+    """One conv pass whose output channels are cut into segments with their own destination and epilogue
+    (include/irr_b200.h irr_conv2d_fwd_multi).  ``segs``: list of dicts ``{n_begin, out, slope=1.0, alpha=1.0,
+    addend=None, pre=False}`` in increasing n_begin (multiples of 16, the first 0); segment i holds channels
+    [n_begin_i, n_begin_{i+1}) and ``out`` must have exactly that many channels."""
+    B, Cin, H, W = x.shape
+    Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
+    px, sx = _v(x, "x")
+    arr = (_lib.ConvSeg * len(segs))()
+    for i, sg in enumerate(segs):
+        n_end = segs[i + 1]["n_begin"] if i + 1 < len(segs) else Cout
+        out = sg["out"]
+        assert out.shape == (B, n_end - sg["n_begin"], Ho, Wo), (tuple(out.shape), (B, n_end - sg["n_begin"], Ho, Wo))
+        po, so = _v(out, f"out[{i}]")
+        add = sg.get("addend")
+        if add is not None:
+            assert add.shape == out.shape
+        pa, sa = (_v(add, f"addend[{i}]") if add is not None else (None, 0))
+        arr[i].n_begin = sg["n_begin"]; arr[i].addend_pre = 1 if sg.get("pre") else 0
+        arr[i].leaky_slope = sg.get("slope", 1.0); arr[i].alpha = sg.get("alpha", 1.0)
+        arr[i].addend = pa; arr[i].addend_bs = sa; arr[i].y = po; arr[i].y_bs = so
+    lib = _lib.load()
+    key = (B, Cin, H, W, Cout, ks, stride, dil, math)
+    nws = _ws_bytes.get(key)
+    if nws is None:
+        nws = lib.irr_conv2d_workspace_bytes(B, Cin, H, W, Cout, ks, stride, dil, math)
+        _ws_bytes[key] = nws
+    ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
+    _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_multi, px, sx,
+            _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), B, Cin, H, W, Cout, ks, stride, dil, arr, len(segs),
+            math, ws.data_ptr() if ws is not None else None, nws, _stream())
+    return [sg["out"] for sg in segs]
+
+
 def resize_ac(x, OH: int, OW: int, out=None, s_even: float = 1.0, s_odd: float = 1.0):
     B, C, H, W = x.shape
     if out is None:

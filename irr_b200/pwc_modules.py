@@ -165,38 +165,56 @@ class _DenseEstimator(nn.Module):
         hi = 448
         fuse = get_conv_math() == ops.MATH_TC_3XF16
         for c, g in zip([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5], self.GROWTH):
-            if fuse and c is self.conv5:
+            if fuse and c is self.conv4:
                 break
             c(buf[:, hi:self.total_ch], out=buf[:, hi - g:hi])
             hi -= g
         if not fuse:
             return self.conv_last(buf[:, 0:self.total_ch], out=out, addend=addend)
-        # conv_last(cat[conv5(x4), x4]) = W_last[:, :32] * conv5(x4) + W_last[:, 32:] * x4 (+ b_last): the x4 part rides
-        # along with conv5 as extra output columns (one pass over the 531/530 channels instead of two), then a
-        # 32-channel conv adds the conv5 part.  Same sums, different association (<= 1e-6).
-        packed_f, bias_f, packed_l, zero_b = self._fused_tail()
+        # Fused tail.  conv5 and conv_last read everything conv4 reads (plus conv4's / conv5's own outputs), and thin
+        # layers cost the same producer time per input channel as fat ones, so the part of conv5 and of conv_last that
+        # sees conv4's input rides along with conv4 as extra output columns (raw partial sums), one pass over the
+        # 467/466 channels instead of three:
+        #   pass B  x = [c3|c2|c1|in]    : conv4 (64, final) | conv5 partial (32) | conv_last partial (+ b_last + addend)
+        #   pass C  x = c4 (64 ch)        : conv5 = lrelu(. + partial + b5) (32, final) | conv_last partial += .
+        #   pass D  x = c5 (32 ch)        : conv_last = partial + .
+        # Same sums, different association (<= 1e-6).
+        (pB, bB), (pC, bC), (pD, bD) = self._fused_tail()
         B, _, H, W = buf.shape
         co = self.ch_out
+        dev = buf.device
         if out is None:
-            out = torch.empty((B, co, H, W), dtype=torch.float32, device=buf.device)
-        partial = torch.empty((B, co, H, W), dtype=torch.float32, device=buf.device)
-        ops.conv2d_dual(buf[:, 32:self.total_ch], packed_f, bias_f, 32 + co, 32, 3, out=buf[:, 0:32], out2=partial,
-                        slope=0.1, slope2=1.0, addend2=addend)
-        return ops.conv2d(buf[:, 0:32], packed_l, zero_b, co, 3, slope=1.0, out=out, addend=partial,
-                          math=ops.MATH_TC_3XF16)
+            out = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
+        p5 = torch.empty((B, 32, H, W), dtype=torch.float32, device=dev)
+        pl = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
+        ops.conv2d_multi(buf[:, 96:self.total_ch], pB, bB, 96 + co, 3, [
+            dict(n_begin=0, out=buf[:, 32:96], slope=0.1),
+            dict(n_begin=64, out=p5, slope=1.0),
+            dict(n_begin=96, out=pl, slope=1.0, addend=addend)])
+        ops.conv2d_multi(buf[:, 32:96], pC, bC, 32 + co, 3, [
+            dict(n_begin=0, out=buf[:, 0:32], slope=0.1, addend=p5, pre=True),
+            dict(n_begin=32, out=pl, slope=1.0, addend=pl)])
+        return ops.conv2d(buf[:, 0:32], pD, bD, co, 3, slope=1.0, out=out, addend=pl, math=ops.MATH_TC_3XF16)
 
     def _fused_tail(self):
-        """Packed weights of the fused conv5 + conv_last tail (cached; rebuilt when a parameter changes)."""
+        """Packed weights / biases of the three fused-tail passes (cached; rebuilt when a parameter changes)."""
+        w4, b4 = self.conv4[0].weight, self.conv4[0].bias
         w5, b5 = self.conv5[0].weight, self.conv5[0].bias
         wl, bl = self.conv_last[0].weight, self.conv_last[0].bias
-        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in (w5, b5, wl, bl))
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in (w4, b4, w5, b5, wl, bl))
         hit = getattr(self, "_fused_cache", None)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                wf = torch.cat([w5, wl[:, 32:]], 0).contiguous()
-                bf = torch.cat([b5, bl], 0).contiguous()
-                hit = (key, (ops.pack_weights(wf, ops.MATH_TC_3XF16), bf,
-                             ops.pack_weights(wl[:, :32].contiguous(), ops.MATH_TC_3XF16), torch.zeros_like(bl)))
+                # channel order of the buffer: [c5 32 | c4 64 | c3 96 | c2 128 | c1 128 | in]; conv4 reads [96:], conv5
+                # reads [32:] (its first 64 input channels are c4), conv_last reads [0:] (c5, then c4, then conv4's input)
+                wB = torch.cat([w4, w5[:, 64:], wl[:, 96:]], 0).contiguous()
+                bB = torch.cat([b4, torch.zeros_like(b5), bl], 0).contiguous()
+                wC = torch.cat([w5[:, :64], wl[:, 32:96]], 0).contiguous()
+                bC = torch.cat([b5, torch.zeros_like(bl)], 0).contiguous()
+                wD = wl[:, :32].contiguous()
+                bD = torch.zeros_like(bl)
+                M = ops.MATH_TC_3XF16
+                hit = (key, ((ops.pack_weights(wB, M), bB), (ops.pack_weights(wC, M), bC), (ops.pack_weights(wD, M), bD)))
             self._fused_cache = hit
         return hit[1]
 

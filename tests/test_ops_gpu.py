@@ -422,6 +422,67 @@ def test_conv2d_3xf16_dual_output(cuda, shape):
     assert (out[:, :3] == 0).all() and (out[:, 35:] == 0).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 467, 20, 64, 2), (1, 466, 7, 16, 1), (2, 147, 33, 39, 2), (16, 467, 28, 64, 2)])
+def test_conv2d_3xf16_multi_segment(cuda, shape):
+    """irr_conv2d_fwd_multi: three output segments with their own destination / activation / residual, one of them with
+    the addend BEFORE the activation (a partial sum of the same layer) — against fp64 convs.  Shapes: TMA-staged, split-K
+    (coarse level), gather variant (odd width), and a many-item launch."""
+    from irr_b200 import ops
+    B, Cin, H, W, co = shape
+    x = torch.from_numpy(rs(81, (B, Cin, H, W)))
+    w = torch.from_numpy(rs(82, (96 + co, Cin, 3, 3))) * float(np.sqrt(2.0 / (Cin * 9)))
+    b = torch.from_numpy(rs(83, (96 + co,))) * 0.1
+    pre = torch.from_numpy(rs(84, (B, 64, H, W)))
+    add3 = torch.from_numpy(rs(85, (B, co, H, W)))
+    full = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+    ref1 = 0.5 * torch.nn.functional.leaky_relu(full[:, :64] + pre.double(), 0.1)     # pre-activation addend, alpha
+    ref2 = full[:, 64:96]                                                             # raw partial sums
+    ref3 = full[:, 96:] + add3.double()                                               # post-activation addend
+    o1 = torch.zeros((B, 70, H, W), device=cuda)
+    o2 = torch.empty((B, 32, H, W), device=cuda)
+    o3 = add3.to(cuda).clone()                                                        # in place: y == addend
+    ops.conv2d_multi(x.to(cuda), ops.pack_weights(w.to(cuda), ops.MATH_TC_3XF16), b.to(cuda), 96 + co, 3, [
+        dict(n_begin=0, out=o1[:, 3:67], slope=0.1, alpha=0.5, addend=pre.to(cuda), pre=True),
+        dict(n_begin=64, out=o2, slope=1.0),
+        dict(n_begin=96, out=o3, slope=1.0, addend=o3)])
+    assert (o1[:, 3:67].cpu().double() - ref1).abs().max().item() <= 1e-4
+    assert (o2.cpu().double() - ref2).abs().max().item() <= 1e-4
+    assert (o3.cpu().double() - ref3).abs().max().item() <= 1e-4
+    assert (o1[:, :3] == 0).all() and (o1[:, 67:] == 0).all()
+
+
+@pytest.mark.parametrize("hw", [(20, 64), (7, 16), (33, 39)])
+@pytest.mark.parametrize("kind", ["flow", "occ"])
+def test_dense_estimator_fused_tail_vs_fp64(cuda, kind, hw):
+    """FlowEstimatorDense / OccEstimatorDense with the fused conv4|conv5|conv_last tail (pwc_modules._DenseEstimator):
+    every dense output and conv_last (+ skip) against an fp64 restatement of models/pwc_modules.py:153-170,190-207."""
+    from irr_b200 import ops, pwc_modules
+    import torch.nn.functional as F
+    H, W = hw
+    est = (pwc_modules.FlowEstimatorDense(115) if kind == "flow" else pwc_modules.OccEstimatorDense(114)).to(cuda).eval()
+    torch.manual_seed(5)
+    for prm in est.parameters():
+        if prm.dim() == 1:
+            prm.data.normal_(0, 0.05)
+    co = est.ch_out
+    x = torch.from_numpy(rs(91, (2, est.ch_in, H, W))) * 0.5
+    skip = torch.from_numpy(rs(92, (2, co, H, W)))
+    cur = x.double()
+    for c in (est.conv1, est.conv2, est.conv3, est.conv4, est.conv5):
+        y = F.leaky_relu(F.conv2d(cur, c[0].weight.detach().cpu().double(), c[0].bias.detach().cpu().double(), padding=1), 0.1)
+        cur = torch.cat([y, cur], 1)
+    ref_last = F.conv2d(cur, est.conv_last[0].weight.detach().cpu().double(), est.conv_last[0].bias.detach().cpu().double(),
+                        padding=1) + skip.double()
+    pwc_modules.set_conv_math(ops.MATH_TC_3XF16)
+    buf = torch.empty((2, est.total_ch, H, W), device=cuda)
+    buf[:, 448:] = x.to(cuda)
+    with torch.no_grad():
+        out = est.forward_into(buf, addend=skip.to(cuda))
+    scale = max(1.0, cur.abs().max().item())
+    assert (buf.cpu().double() - cur).abs().max().item() <= 1e-4 * scale
+    assert (out.cpu().double() - ref_last).abs().max().item() <= 1e-4 * max(1.0, ref_last.abs().max().item())
+
+
 def test_conv2d_3xf16_slices_addend(cuda):
     from irr_b200 import ops
     B, Ct, H, W = 2, 100, 20, 36
