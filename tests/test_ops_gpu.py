@@ -445,9 +445,11 @@ def test_conv2d_3xf16_multi_segment(cuda, shape):
         dict(n_begin=0, out=o1[:, 3:67], slope=0.1, alpha=0.5, addend=pre.to(cuda), pre=True),
         dict(n_begin=64, out=o2, slope=1.0),
         dict(n_begin=96, out=o3, slope=1.0, addend=o3)])
-    assert (o1[:, 3:67].cpu().double() - ref1).abs().max().item() <= 1e-4
-    assert (o2.cpu().double() - ref2).abs().max().item() <= 1e-4
-    assert (o3.cpu().double() - ref3).abs().max().item() <= 1e-4
+    # same gate as test_conv2d_3xf16_vs_torch_cpu: the residual is the tensor core's fp32 accumulator, relative ~2e-5
+    tol = lambda ref: 5e-5 * max(2.0, ref.abs().max().item())
+    assert (o1[:, 3:67].cpu().double() - ref1).abs().max().item() <= tol(full[:, :64])
+    assert (o2.cpu().double() - ref2).abs().max().item() <= tol(ref2)
+    assert (o3.cpu().double() - ref3).abs().max().item() <= tol(ref3)
     assert (o1[:, :3] == 0).all() and (o1[:, 67:] == 0).all()
 
 

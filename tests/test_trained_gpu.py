@@ -197,7 +197,11 @@ def test_install_runs_unmodified_reference_model_on_our_kernels(cuda, refmodels)
         R0 = _ref_forward(refmodels, "IRR_PWC", sd, i1, i2, cuda)
         with _backend(True, False):
             R1 = _ref_forward(refmodels, "IRR_PWC", sd, i1, i2, cuda)
-        floor = max(_epe(R0["flow"], R1["flow"]), ABS_FLOOR)
+        with _cuda_shim():
+            Rcpu = _ref_forward(refmodels, "IRR_PWC", sd, i1, i2, torch.device("cpu"))
+        # what the reference differs from itself by (cudnn.benchmark on/off, GPU vs host): with trained weights the hard
+        # warp mask amplifies 1e-7 differences to ~5e-2 px (profiles/r02_parity_trained.txt)
+        floor = max(_epe(R0["flow"], R1["flow"]), _epe(R0["flow"], Rcpu["flow"]), ABS_FLOOR)
         existing = refmodels.IRR_PWC(None)
         existing.load_state_dict(sd)
         existing = existing.to(cuda).eval()
