@@ -33,6 +33,9 @@ PROTOTYPES = {
     "irr_correlation_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_fp],
     "irr_warp_correlation_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i,
                                  c_i, c_f, c_i, c_i, c_f, c_i, c_fp],
+    "irr_correlation_workspace_bytes": [c_i, c_i, c_i, c_i],
+    "irr_warp_correlation_fwd_ws": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i,
+                                    c_i, c_f, c_i, c_i, c_f, c_i, c_fp, C.c_size_t, c_fp],
     "irr_warp_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_i, c_i, c_i,
                      c_f, c_i, c_i, c_fp],
     "irr_correlation_generic_fwd": [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
@@ -61,7 +64,7 @@ PROTOTYPES = {
     "irr_refine_gather_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
 }
 _RESTYPES = {"irr_last_error": C.c_char_p, "irr_conv2d_packed_bytes": C.c_size_t,
-             "irr_conv2d_workspace_bytes": C.c_size_t}
+             "irr_conv2d_workspace_bytes": C.c_size_t, "irr_correlation_workspace_bytes": C.c_size_t}
 
 _lib = None
 

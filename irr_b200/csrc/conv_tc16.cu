@@ -576,25 +576,31 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
         }
         const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
         float* ywr = p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix;  // raw split-K partials
+        // output segments (fused tails of the dense estimators): every 16-channel group belongs to one segment with its
+        // own destination, residual and activation — resolved once per segment, not per group; raw split-K partials keep
+        // the single [Cout] layout
+        int c0 = 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 16) {
-          const int nb = nt * N + c0;
-          const int nvalid = min(16, p.Cout - nb);  // warp-uniform; < 16 only in the layer's last channel group
-          if (nvalid <= 0) break;
-          // output segments (fused tails of the dense estimators): each 16-channel group belongs to one segment with its
-          // own destination, residual and activation; raw split-K partials keep the single [Cout] layout
+        while (c0 < N && nt * N + c0 < p.Cout) {
           int si = 0;
 #pragma unroll
           for (int k = 1; k < H_MAXSEG; ++k)
-            if (k < p.seg.n && nb >= p.seg.s[k].n_begin) si = k;
+            if (k < p.seg.n && nt * N + c0 >= p.seg.s[k].n_begin) si = k;
           const HSeg& sg = p.seg.s[si];
-          const int cb = raw ? nb : nb - sg.n_begin;
+          const int seg_end = (si + 1 < p.seg.n ? p.seg.s[si + 1].n_begin : p.Cout) - nt * N;  // exclusive, inside the tile
+          const int c_end = min(N, seg_end);
+          const int n_off = raw ? 0 : sg.n_begin;
           const float* ap = (sg.addend != nullptr && !raw) ? sg.addend + (size_t)ob * sg.a_bs + opix : nullptr;
           const bool has_add = ap != nullptr;
           const bool pre = sg.pre != 0;
           float* yp = raw ? ywr : sg.y + (size_t)ob * sg.y_bs + opix;
           const float slope = sg.slope;
           const float alpha = sg.alpha;
+#pragma unroll 1
+          for (; c0 < c_end; c0 += 16) {
+          const int nb = nt * N + c0;
+          const int nvalid = min(16, p.Cout - nb);  // warp-uniform; < 16 only in the layer's last channel group
+          const int cb = nb - n_off;
           // residual / skip operand: 16 independent loads in flight before the accumulator is touched
           float add[16];
 #pragma unroll
@@ -629,6 +635,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
             }
           }
           H_ACC(3);
+          }
         }
       }
       h_fence_before();
@@ -682,6 +689,7 @@ struct RArgs {
   int B, Cin, H, W, Cout, n_tile;
   int L, segs, xtiles, items;
   float slope, alpha;
+  int unordered;   // debug A/B only (IRR_ROLL_UNORDERED=1): skip the tap-row order tokens (results then vary in the last ulp)
 };
 
 template <int NG, bool CTR>
@@ -849,7 +857,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
             // bit-determinism: the ky = 0 group of this output row (issued one staged row earlier by warp 8) must have
             // been accumulated before ky = 1 adds to it, and ky = 1 before ky = 2.  The predecessor finished a whole
             // producer row (~1600 clk) ago in steady state, so this wait is almost always already satisfied.
-            if (ky > 0) mbar_wait(ord(ky - 1, slot), (uint32_t)((og >> 2) & 1));
+            if (ky > 0 && !p.unordered) mbar_wait(ord(ky - 1, slot), (uint32_t)((og >> 2) & 1));
           }
           h_fence_after();
           H_ACC(1);
@@ -1229,6 +1237,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
     r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
     r.B = B; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.n_tile = g.n_tile;
     r.slope = slope; r.alpha = alpha;
+    { const char* e = getenv("IRR_ROLL_UNORDERED"); r.unordered = (e && e[0] == '1') ? 1 : 0; }
     r.xtiles = (W + 127) / 128;
     int L = 32;
     while (L > 4 && (long long)B * r.xtiles * ((H + L - 1) / L) < 3LL * sm_count()) L >>= 1;

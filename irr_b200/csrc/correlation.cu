@@ -84,15 +84,27 @@ struct NoTileHook {
   __device__ __forceinline__ void setup(int, int) const {}
 };
 
-template <int NS, bool PREFETCH, class Hook>
+// Channel split for launches with far fewer tiles than SMs (the 7x16 ... 14x32 pyramid levels: 16-32 tiles, up to 25
+// serial 8-channel chunks each): the chunks of a tile are dealt to `ksplit` CTAs ("virtual tiles" vt = tile * ksplit +
+// ks, chunk range [ks*cps, (ks+1)*cps)), each stores its RAW partial sums to workspace slice ks, and corr_split_finish
+// adds the slices in a fixed order, scales by 1/C and applies the LeakyReLU — deterministic, like the convs' split-K.
+struct CSplit {
+  int ksplit, cps;
+  float* ws; long long ws_stride;   // [ksplit][B][81][H][W]
+};
+
+template <int NS, bool PREFETCH, class Hook, bool SPLIT = false>
 __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem, uint32_t full0, uint32_t empty0,
                                              const float* __restrict__ f1, long long f1_bs,
                                              const float* __restrict__ f2, long long f2_bs, float* __restrict__ out,
                                              long long out_bs, int B, int C, int H, int W, int shift, float slope,
-                                             int vec_ok, int tiles_x, int tiles_y, int ntiles, int ctr = 0) {
+                                             int vec_ok, int tiles_x, int tiles_y, int ntiles, int ctr = 0,
+                                             CSplit sp = CSplit{1, 0, nullptr, 0}) {
   const int tid = threadIdx.x;
   const int HW = H * W;
   const int nchunks = (C + CC - 1) / CC;
+  const int ksplit = SPLIT ? sp.ksplit : 1;
+  const int nvt = ntiles * ksplit;
   const bool con = ctr && blockIdx.x == 0 && tid == 0;
   const long long ct0 = con ? clock64() : 0;
   // Thread -> (tile row r, displacement row dyi, 8-pixel strip s8).  The 72 (r, dyi) pairs are dealt to the 9 warps
@@ -116,15 +128,17 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     dyi = h - r;  // 0..8 -> dy = dyi - 4
   }
   int gchunk = 0, it = 0;
-  if ((int)blockIdx.x < ntiles) hook.setup(blockIdx.x, 0);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  if ((int)blockIdx.x < nvt) hook.setup((int)blockIdx.x / ksplit, 0);
+  for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
+    const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
+    const int c_lo = SPLIT ? ks * sp.cps : 0, c_hi = SPLIT ? min(nchunks, c_lo + sp.cps) : nchunks;
     const int tx = tile % tiles_x;
     const int ty = (tile / tiles_x) % tiles_y;
     const int b = tile / (tiles_x * tiles_y);
     const int y0 = ty * TH, x0 = tx * TW;
     {
       const long long t0 = con ? clock64() : 0;
-      if (tile + (int)gridDim.x < ntiles) hook.setup(tile + (int)gridDim.x, it + 1);  // accumulators are dead here
+      if (vt + (int)gridDim.x < nvt) hook.setup((vt + (int)gridDim.x) / ksplit, it + 1);  // accumulators are dead here
       if (con) corr_ctr[1] += (unsigned long long)(clock64() - t0);
     }
     float acc[ND][PX];
@@ -160,7 +174,7 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
       }
     }
 
-    for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+    for (int ci = c_lo; ci < c_hi; ++ci, ++gchunk) {
       const int s = gchunk % NS;
       const uint32_t ph = (uint32_t)((gchunk / NS) & 1);
       mbar_wait_ctr(full0 + 8u * s, ph, con, 0);
@@ -191,7 +205,26 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     const long long te0 = con ? clock64() : 0;
     const int gy = y0 + r;
     const int gx = x0 + s8 * PX;
-    if (gy < H && gx < W) {
+    if (SPLIT) {
+      // channel-split launch: raw partial sums of chunks [c_lo, c_hi) into this split's workspace slice
+      if (gy < H && gx < W) {
+        float* op = sp.ws + (size_t)ks * sp.ws_stride + ((size_t)b * (ND * ND) + (size_t)(dyi * ND)) * HW + (size_t)gy * W + gx;
+        if ((W & 3) == 0 && gx + PX <= W) {
+#pragma unroll
+          for (int d = 0; d < ND; ++d) {
+            float4* q = reinterpret_cast<float4*>(op + (size_t)d * HW);
+            q[0] = make_float4(acc[d][0], acc[d][1], acc[d][2], acc[d][3]);
+            q[1] = make_float4(acc[d][4], acc[d][5], acc[d][6], acc[d][7]);
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < ND; ++d)
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+              if (gx + p < W) op[(size_t)d * HW + p] = acc[d][p];
+        }
+      }
+    } else if (gy < H && gx < W) {
       const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
       float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
       // scale in place first, then issue the stores back to back (a temporary per displacement makes every store
@@ -588,14 +621,16 @@ struct TapSetup {
   }
 };
 
-template <bool FUSED>
+template <bool FUSED, bool SPLIT>
 __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     corr_tma_kernel(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                     const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                     const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
                     GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
-                    int ntiles, int ctr) {
+                    int ntiles, int ctr, CSplit sp) {
   constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
+  const int ksplit = SPLIT ? sp.ksplit : 1;
+  const int nvt = ntiles * ksplit;
   extern __shared__ __align__(1024) float smem[];
   float* fpr = smem + NS * STAGE_ELEMS;                          // footprint ring (FUSED)
   float* tab = fpr + (FUSED ? T_NFS * FP_ELEMS : 0);             // tap tables (FUSED)
@@ -633,18 +668,20 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       TapSetup hook;
       hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.tiles_x = tiles_x;
       hook.tiles_y = tiles_y; hook.tab = tab; hook.meta = meta; hook.red = red; hook.tabfull0 = tabfull(0);
-      corr_compute<NS, false>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
-                              vec_ok, tiles_x, tiles_y, ntiles, ctr);
+      corr_compute<NS, false, TapSetup, SPLIT>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W,
+                                               shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
     } else {
-      corr_compute<NS, false>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift,
-                              slope, vec_ok, tiles_x, tiles_y, ntiles, ctr);
+      corr_compute<NS, false, NoTileHook, SPLIT>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B,
+                                                 C, H, W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
     }
   } else if (tid == (FUSED ? T_ISSUER_FUSED : NCOMP)) {
     // ============================== COPY ISSUER (one thread) ==============================
     int gchunk = 0, it = 0;
     const bool con = ctr && blockIdx.x == 0;
     const long long ct0 = con ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
+      const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
+      const int c_lo = SPLIT ? ks * sp.cps : 0, c_hi = SPLIT ? min(nchunks, c_lo + sp.cps) : nchunks;
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
       const int b = tile / (tiles_x * tiles_y);
@@ -657,7 +694,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         const volatile int* mt = meta + 4 * (it & 1);
         oy = mt[0]; ox = mt[1]; foot = mt[2];
       }
-      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+      for (int ci = c_lo; ci < c_hi; ++ci, ++gchunk) {
         const int s = gchunk % NS;
         mbar_wait_ctr(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1), con, 9);
         const uint32_t st = smem_u32(smem + s * STAGE_ELEMS);
@@ -687,7 +724,9 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     int gchunk = 0, it = 0;
     const bool con = ctr && blockIdx.x == 0 && pt == 0;
     const long long ct0 = con ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
+      const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
+      const int c_lo = SPLIT ? ks * sp.cps : 0, c_hi = SPLIT ? min(nchunks, c_lo + sp.cps) : nchunks;
       const int b = tile / (tiles_x * tiles_y);
       int b2 = b + shift;
       if (b2 >= B) b2 -= B;
@@ -708,7 +747,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
           od[k] = h < NHALO ? to[h] : -1;
         }
       }
-      for (int ci = 0; ci < nchunks; ++ci, ++gchunk) {
+      for (int ci = c_lo; ci < c_hi; ++ci, ++gchunk) {
         const int s = gchunk % NS, fs = gchunk % T_NFS;
         mbar_wait_ctr(fpfull(fs), (uint32_t)((gchunk / T_NFS) & 1), con, 17);
         mbar_wait_ctr(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1), con, 18);
@@ -817,6 +856,45 @@ __global__ void corr_generic_kernel(const float* __restrict__ in1, const float* 
   out[i] = acc / (float)(ks * ks * C);
 }
 
+// out = act((1/C) * sum_ks ws[ks]) — the channel-split launches' second pass (fixed summation order: deterministic).
+__global__ void corr_split_finish(const float* __restrict__ ws, long long ws_stride, int ksplit, float* __restrict__ out,
+                                  long long out_bs, int HW, long long total, float inv_c, float slope) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float acc = 0.f;
+  for (int k = 0; k < ksplit; ++k) acc += __ldg(ws + (size_t)k * ws_stride + i);
+  const long long per = (long long)(ND * ND) * HW;
+  const long long b = i / per;
+  out[(size_t)b * out_bs + (size_t)(i - b * per)] = leaky(acc * inv_c, slope);
+}
+
+// Channel-split plan: only when the launch has at most half as many tiles as the GPU has SMs and >= 2 chunks.
+static int corr_ksplit(int ntiles, int nchunks, int* cps_out) {
+  int ksplit = 1, cps = nchunks;
+  const int sms = sm_count();
+  if (nchunks >= 2 && ntiles * 2 <= sms) {
+    int want = sms / ntiles;
+    if (want > nchunks) want = nchunks;
+    cps = (nchunks + want - 1) / want;
+    ksplit = (nchunks + cps - 1) / cps;
+  }
+  *cps_out = cps;
+  return ksplit;
+}
+static bool corr_no_split() {  // IRR_CORR_NO_SPLIT=1: never split channels (A/B measurements)
+  const char* e = getenv("IRR_CORR_NO_SPLIT");
+  return e && e[0] == '1';
+}
+
+size_t corr_workspace_bytes(int B, int C, int H, int W) {
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const long long nt = (long long)tiles_x * tiles_y * B;
+  if (nt > 0x7fffffffLL) return 0;
+  int cps;
+  const int k = corr_ksplit((int)nt, (C + CC - 1) / CC, &cps);
+  return k > 1 ? (size_t)k * B * (ND * ND) * H * W * sizeof(float) : 0;
+}
+
 static bool corr_no_tma() {  // IRR_CORR_NO_TMA=1: force the cp.async kernel (A/B measurements, tests of the fallback)
   const char* e = getenv("IRR_CORR_NO_TMA");
   return e && e[0] == '1';
@@ -830,7 +908,7 @@ static bool corr_ctr_on() {  // IRR_CORR_CTR=1: role cycle counters (debug)
 template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
-                       int C, int H, int W, int shift, float slope, cudaStream_t st) {
+                       int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int CORR_SMEM = FUSED ? CORR_SMEM_FUSED : CORR_SMEM_PLAIN;
   static SmemAttrCache attr = {};
   if (int rc = ensure_dyn_smem(corr_kernel<FUSED>, CORR_SMEM, attr, fn)) return rc;
@@ -847,20 +925,45 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
   if (vec_in && !corr_no_tma()) {
     constexpr int TSMEM = FUSED ? CORR_SMEM_TMA_FUSED : CORR_SMEM_TMA_PLAIN;
-    static SmemAttrCache tattr = {};
+    static SmemAttrCache tattr = {}, tattr_split = {};
     CUtensorMap m1, m2;
     if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC) &&
         make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC)) {
-      if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED>, TSMEM, tattr, fn)) return rc;
       const int ctr = corr_ctr_on() ? 1 : 0;
       if (ctr) {
         static const unsigned long long zeros[32] = {0};
         cudaMemcpyToSymbolAsync(corr_ctr, zeros, sizeof(zeros), 0, cudaMemcpyHostToDevice, st);
       }
-      corr_tma_kernel<FUSED><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(
-          m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,
-          ntiles, ctr);
-      return check_launch(fn);
+      CSplit sp = {1, 0, nullptr, 0};
+      if (ws != nullptr && !corr_no_split() && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+        int cps;
+        const int k = corr_ksplit(ntiles, (C + CC - 1) / CC, &cps);
+        const size_t slice = (size_t)B * (ND * ND) * H * W;
+        if (k > 1 && (size_t)k * slice * sizeof(float) <= ws_bytes) {
+          sp.ksplit = k; sp.cps = cps; sp.ws = reinterpret_cast<float*>(ws); sp.ws_stride = (long long)slice;
+          const long long nvt = (long long)ntiles * k;
+          grid = nvt < sm_count() ? (int)nvt : sm_count();
+        }
+      }
+      if (sp.ksplit > 1) {
+        if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, true>, TSMEM, tattr_split, fn)) return rc;
+        corr_tma_kernel<FUSED, true><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(
+            m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,
+            ntiles, ctr, sp);
+      } else {
+        if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, false>, TSMEM, tattr, fn)) return rc;
+        corr_tma_kernel<FUSED, false><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(
+            m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,
+            ntiles, ctr, sp);
+      }
+      if (int rc = check_launch(fn)) return rc;
+      if (sp.ksplit > 1) {
+        const long long total = (long long)B * (ND * ND) * H * W;
+        corr_split_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sp.ws, sp.ws_stride, sp.ksplit, out, out_bs, H * W,
+                                                                          total, 1.0f / (float)C, slope);
+        return check_launch(fn);
+      }
+      return 0;
     }
   }
   corr_kernel<FUSED><<<grid, CORR_THREADS, CORR_SMEM, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H,
@@ -884,7 +987,33 @@ int irr_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long 
   IRR_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < B, fn, "f2_batch_shift out of range");
   GridArgs g = make_grid_args(nullptr, nullptr, H, W, H, W, 1.f, 0);
   return launch_corr<false>(fn, f1, f1_bs, f2, f2_bs, nullptr, 0, out, out_bs, g, B, C, H, W, f2_batch_shift,
-                            leaky_slope, as_stream(stream));
+                            leaky_slope, nullptr, 0, as_stream(stream));
+}
+
+size_t irr_correlation_workspace_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return corr_workspace_bytes(B, C, H, W);
+}
+
+int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,
+                                long long flow_bs, const float* lin_x, const float* lin_y, float* out, long long out_bs,
+                                int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
+                                int f2_batch_shift, float leaky_slope, int grid_flags, void* workspace,
+                                size_t workspace_bytes, irr_stream_t stream) {
+  const char* fn = "irr_warp_correlation_fwd_ws";
+  IRR_REQUIRE(f1 && f2 && out, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, fn, "non-positive size");
+  IRR_REQUIRE(max_disp == MD, fn, "only max_disp == 4 is compiled");
+  IRR_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < B, fn, "f2_batch_shift out of range");
+  if (flow == nullptr) {  // no warp: the plain cost volume
+    GridArgs g = make_grid_args(nullptr, nullptr, H, W, H, W, 1.f, 0);
+    return launch_corr<false>(fn, f1, f1_bs, f2, f2_bs, nullptr, 0, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
+                              workspace, workspace_bytes, as_stream(stream));
+  }
+  IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
+  GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
+  return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
+                           workspace, workspace_bytes, as_stream(stream));
 }
 
 int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,
@@ -898,7 +1027,7 @@ int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, 
   IRR_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < B, fn, "f2_batch_shift out of range");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
   return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift,
-                           leaky_slope, as_stream(stream));
+                           leaky_slope, nullptr, 0, as_stream(stream));
 }
 
 // Debug hook (not part of the ABI in include/irr_b200.h), scripts/corr_counters.py

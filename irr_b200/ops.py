@@ -104,6 +104,19 @@ def _new(like: torch.Tensor, C: int, H: int, W: int) -> torch.Tensor:
     return torch.empty((like.shape[0], C, H, W), dtype=torch.float32, device=like.device)
 
 
+_corr_ws_bytes = {}
+
+
+def _corr_workspace(B, C, H, W, device):
+    """Scratch for the channel-split plan of coarse-level cost volumes (0 bytes = this shape is never split)."""
+    key = (B, C, H, W)
+    n = _corr_ws_bytes.get(key)
+    if n is None:
+        n = _lib.load().irr_correlation_workspace_bytes(B, C, H, W)
+        _corr_ws_bytes[key] = n
+    return (torch.empty(n // 4, dtype=torch.float32, device=device), n) if n else (None, 0)
+
+
 def correlation(f1, f2, out=None, shift: int = 0, slope: float = 1.0, max_disp: int = 4):
     B, C, H, W = f1.shape
     assert f2.shape == f1.shape
@@ -112,8 +125,13 @@ def correlation(f1, f2, out=None, shift: int = 0, slope: float = 1.0, max_disp: 
         out = _new(f1, D, H, W)
     assert out.shape == (B, D, H, W)
     p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); po, so = _v(out, "out")
-    _launch("correlation", (B, C, H, W), _lib.load().irr_correlation_fwd, p1, s1, p2, s2, po, so, B, C, H, W, max_disp,
-            shift, slope, _stream())
+    ws, nws = _corr_workspace(B, C, H, W, f1.device)
+    if ws is None:
+        _launch("correlation", (B, C, H, W), _lib.load().irr_correlation_fwd, p1, s1, p2, s2, po, so, B, C, H, W, max_disp,
+                shift, slope, _stream())
+    else:
+        _launch("correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, None, 0, None, None,
+                po, so, B, C, H, W, H, W, 1.0, max_disp, shift, slope, 0, ws.data_ptr(), nws, _stream())
     return out
 
 
@@ -127,9 +145,10 @@ def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: floa
     lx = host_linspace(W, f1.device) if lin_x is None else lin_x
     ly = host_linspace(H, f1.device) if lin_y is None else lin_y
     p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
-    _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd, p1, s1, p2, s2, pf, sf,
+    ws, nws = _corr_workspace(B, C, H, W, f1.device)
+    _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, pf, sf,
             _p(lx, "lin_x", f1, W), _p(ly, "lin_y", f1, H), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp,
-            shift, slope, _grid_mode, _stream())
+            shift, slope, _grid_mode, ws.data_ptr() if ws is not None else None, nws, _stream())
     return out
 
 

@@ -210,6 +210,38 @@ def test_cost_volume_full_size_properties(cuda):
         del os.environ["IRR_CORR_NO_TMA"]
 
 
+@pytest.mark.parametrize("shape", [(16, 196, 7, 16), (16, 128, 14, 32), (2, 196, 7, 16), (2, 96, 28, 64), (1, 20, 9, 40)])
+def test_cost_volume_channel_split(cuda, shape):
+    """Coarse pyramid levels: the channel chunks of a tile are dealt to several CTAs and a second launch adds the partial
+    sums in a fixed order (irr_warp_correlation_fwd_ws).  Plain and fused, against the un-split kernel (same products,
+    different association: <= 1e-6), against the oracle, and bit-reproducible from run to run."""
+    import os
+    from irr_b200 import ops, _lib
+    B, C, H, W = shape
+    f1 = dev(rs(41, (B, C, H, W)), cuda)
+    f2 = dev(rs(42, (B, C, H, W)), cuda)
+    flow = dev(rs(43, (B, 2, H, W)), cuda) * 0.3
+    nws = _lib.load().irr_correlation_workspace_bytes(B, C, H, W)
+    if shape[0] * ((H + 7) // 8) * ((W + 31) // 32) * 2 <= 148 and C > 8:
+        assert nws > 0      # these launches are split on a 148-SM part
+    a = ops.correlation(f1, f2, shift=B // 2, slope=0.1)
+    fz = ops.warp_correlation(f1, f2, flow, 16 * H, 16 * W, 0.05, shift=B // 2, slope=0.1)
+    assert torch.equal(a, ops.correlation(f1, f2, shift=B // 2, slope=0.1))
+    assert torch.equal(fz, ops.warp_correlation(f1, f2, flow, 16 * H, 16 * W, 0.05, shift=B // 2, slope=0.1))
+    os.environ["IRR_CORR_NO_SPLIT"] = "1"
+    try:
+        a0 = ops.correlation(f1, f2, shift=B // 2, slope=0.1)
+        fz0 = ops.warp_correlation(f1, f2, flow, 16 * H, 16 * W, 0.05, shift=B // 2, slope=0.1)
+    finally:
+        del os.environ["IRR_CORR_NO_SPLIT"]
+    assert (a - a0).abs().max().item() <= 1e-6 and (fz - fz0).abs().max().item() <= 1e-6
+    ref = torch.nn.functional.leaky_relu(O.cost_volume(f1.cpu(), torch.roll(f2.cpu(), -(B // 2), 0)), 0.1)
+    assert (a.cpu() - ref).abs().max().item() <= 1e-5
+    refw = torch.nn.functional.leaky_relu(
+        O.cost_volume(f1.cpu(), O.warp(torch.roll(f2.cpu(), -(B // 2), 0), flow.cpu(), 16 * H, 16 * W, 0.05)), 0.1)
+    assert (fz.cpu() - refw).abs().max().item() <= 1e-4
+
+
 # ------------------------------------------------------------------ conv
 CONV_CASES = [
     # (B, Cin, H, W, Cout, k, stride, dil)
