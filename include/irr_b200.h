@@ -212,6 +212,15 @@ int irr_correlation_bwd(const float* f1, long long f1_bs, const float* f2, long 
                         long long go_bs, float* grad_f1, long long g1_bs, float* grad_f2, long long g2_bs, int B, int C,
                         int H, int W, int max_disp, irr_stream_t stream);
 
+/* §8(f).4 — backward of WarpingLayer.forward (models/pwc_modules.py:119-133; autograd through grid_sample with the hard
+ * mask as a constant): grad_x[b,c,tap] += mask * w_tap * grad_out[b,c,y,x] (atomic adds — zero-fill grad_x first),
+ * grad_flow[b,0/1,y,x] = mask * sum_c grad_out * d(bilinear)/d(ix,iy) * (dim-1)/max(dim_im-1,1)/div_flow (zero-fill
+ * grad_flow first).  Either gradient may be NULL.  No batch rotation (autograd use only). */
+int irr_warp_bwd(const float* x, long long x_bs, const float* flow, long long flow_bs, const float* lin_x,
+                 const float* lin_y, const float* grad_out, long long go_bs, float* grad_x, long long gx_bs,
+                 float* grad_flow, long long gf_bs, int B, int C, int H, int W, int H_im, int W_im, float div_flow,
+                 int grid_flags, irr_stream_t stream);
+
 /* §8(f).1 — evaluation metrics of the reference's eval-mode losses (losses.py:8-10, 24-37, 634-636, 688-697), one
  * launch per batch, deterministic.  flow / target: B x 2 x H x W; valid, occ_logits, target_occ: B x 1 x H x W or NULL.
  * sums: B x 8 float64 = { S epe*valid, S valid, S outlier, S pred*true, S pred, S true, 0, 0 } with

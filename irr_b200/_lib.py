@@ -38,6 +38,8 @@ PROTOTYPES = {
                                     c_i, c_f, c_i, c_i, c_f, c_i, c_fp, C.c_size_t, c_fp],
     "irr_warp_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_i, c_i, c_i,
                      c_f, c_i, c_i, c_fp],
+    "irr_warp_bwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
+                     c_i, c_fp],
     "irr_correlation_generic_fwd": [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_correlation_generic_out_shape": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, C.POINTER(c_i), C.POINTER(c_i),
                                           C.POINTER(c_i)],

@@ -12,10 +12,10 @@ Ordering: ``WarpingLayer`` is a CLASS the reference instantiates in each model's
 already exists call ``install(models_pkg, model=that_model)`` (or ``patch_instances(model)``): every sub-module whose
 class is named ``WarpingLayer`` gets the new forward bound on the instance.
 
-Autograd: the irr_b200 warp / resize kernels are inference kernels (no ``grad_fn``).  The installed functions therefore
-check ``torch.is_grad_enabled()`` and the inputs' ``requires_grad``: when a gradient is wanted, the cost volume goes
-through ``CorrelationFunction`` (``irr_correlation_bwd``) and the warp / resize calls are handed back to the reference's
-ORIGINAL implementations (kept at install time), so a reference model in train mode keeps back-propagating.
+Autograd: the installed functions check ``torch.is_grad_enabled()`` and the inputs' ``requires_grad``: when a gradient
+is wanted, the cost volume goes through ``CorrelationFunction`` (``irr_correlation_bwd``), the warp through
+``WarpFunction`` (``irr_warp_bwd``), and the bilinear resize is handed back to the reference's ORIGINAL implementation
+(kept at install time), so a reference model in train mode keeps back-propagating.
 ``uninstall()`` restores every patched name.
 """
 from __future__ import annotations
@@ -56,11 +56,7 @@ def upsample2d_as(inputs, target_as, mode="bilinear"):
 
 def _warp_forward(self, x, flow, height_im, width_im, div_flow):
     if _wants_grad(x, flow):
-        orig = _originals.get("WarpingLayer")
-        if orig is None:
-            raise RuntimeError("irr_b200.install: the warp kernel is inference-only and no reference WarpingLayer was "
-                               "saved to fall back to")
-        return orig.forward(self, x, flow, height_im, width_im, div_flow)
+        return P.WarpFunction.apply(x, flow, height_im, width_im, div_flow)   # irr_warp_fwd / irr_warp_bwd
     return P.ops.warp(x.contiguous(), flow.contiguous(), height_im, width_im, div_flow)
 
 

@@ -168,6 +168,24 @@ def warp(x, flow, height_im: int, width_im: int, div_flow: float, out=None, minu
     return out
 
 
+def warp_backward(x, flow, grad_out, height_im: int, width_im: int, div_flow: float, need_x: bool = True,
+                  need_flow: bool = True, lin_x=None, lin_y=None):
+    """(grad_x, grad_flow) of ``warp(x, flow)`` (no batch rotation, no minuend) — include/irr_b200.h irr_warp_bwd.  The
+    hard mask is a constant, as under autograd in the reference.  A gradient that is not needed is None."""
+    B, C, H, W = x.shape
+    assert flow.shape == (B, 2, H, W) and tuple(grad_out.shape) == (B, C, H, W)
+    gx = torch.zeros_like(x) if need_x else None
+    gf = torch.zeros((B, 2, H, W), dtype=torch.float32, device=x.device) if need_flow else None
+    lx = host_linspace(W, x.device) if lin_x is None else lin_x
+    ly = host_linspace(H, x.device) if lin_y is None else lin_y
+    px, sx = _v(x, "x"); pf, sf = _v(flow, "flow"); pg, sg = _v(grad_out, "grad_out")
+    qx, tx = _v(gx, "grad_x") if gx is not None else (None, 0)
+    qf, tf = _v(gf, "grad_flow") if gf is not None else (None, 0)
+    _launch("warp_bwd", (B, C, H, W), _lib.load().irr_warp_bwd, px, sx, pf, sf, _p(lx, "lin_x", x, W), _p(ly, "lin_y", x, H),
+            pg, sg, qx, tx, qf, tf, B, C, H, W, height_im, width_im, div_flow, _grid_mode, _stream())
+    return gx, gf
+
+
 def correlation_generic(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
     import ctypes
     B, C, H, W = in1.shape

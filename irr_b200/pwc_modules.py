@@ -59,8 +59,38 @@ class ConvBlock(nn.Sequential):
 
     def forward(self, x, out=None, addend=None, alpha=1.0):
         math = self._math()
-        return ops.conv2d(x, self.packed(math), self[0].bias, self.cout, self.ks, self.stride, self.dil,
+        w, b = self[0].weight, self[0].bias
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+            if out is not None or addend is not None or alpha != 1.0:
+                raise RuntimeError("irr_b200.conv: the fused out= / addend= / alpha forms are inference-only")
+            return _ConvFunction.apply(x, w, b, self, math)
+        return ops.conv2d(x, self.packed(math), b, self.cout, self.ks, self.stride, self.dil,
                           slope=self.slope, out=out, addend=addend, alpha=alpha, math=math)
+
+
+class _ConvFunction(torch.autograd.Function):
+    """conv() under autograd: the forward is the irr_b200 kernel; the backward (not on the inference
+    hot path, no kernel of ours) goes through ATen's convolution_backward on the LeakyReLU-masked gradient — the sign of
+    the output equals the sign of the pre-activation for any positive slope, so nothing but y has to be kept."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, block, math):
+        x = x.contiguous()
+        y = ops.conv2d(x, block.packed(math), b, block.cout, block.ks, block.stride, block.dil, slope=block.slope, math=math)
+        ctx.save_for_backward(x, w, y)
+        ctx.block = block
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        blk = ctx.block
+        g = gy if blk.slope == 1.0 else gy * torch.where(y > 0, 1.0, blk.slope).to(gy.dtype)
+        pad = ((blk.ks - 1) * blk.dil) // 2
+        gx, gw, gb = torch.ops.aten.convolution_backward(
+            g.contiguous(), x, w, [blk.cout], [blk.stride] * 2, [pad] * 2, [blk.dil] * 2, False, [0, 0], 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
+        return gx, gw, gb, None, None
 
 
 def conv(in_planes, out_planes, kernel_size=3, stride=1, dilation=1, isReLU=True):
@@ -95,10 +125,31 @@ def flow_scales(h, w, div_flow, width_im, height_im, to_local=True):
     return float(width_im * div_flow / w), float(height_im * div_flow / h)
 
 
+class _ScaleChannels(torch.autograd.Function):
+    """y[:, c] = x[:, c] * (s_even if c even else s_odd) on the irr_b200 kernel, differentiable (the backward is the
+    same scaling of the incoming gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, s_even, s_odd):
+        ctx.scales = (s_even, s_odd)
+        return ops.scale_channels(x.contiguous(), s_even=s_even, s_odd=s_odd)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.scale_channels(g.contiguous(), s_even=ctx.scales[0], s_odd=ctx.scales[1]), None, None
+
+
 def rescale_flow(flow, div_flow, width_im, height_im, to_local=True):
-    """models/pwc_modules.py:70-82, including its in-place side effect on ``flow``: the argument is
-    scaled in place AND a new tensor with the same values is returned."""
+    """models/pwc_modules.py:70-82.
+
+    Without autograd (inference) it keeps the reference's in-place side effect on ``flow``: the argument
+    is scaled in place AND a new tensor with the same values is returned — IRR_PWC's eval forward depends on it
+    (IRR_PWC.py:128-129).  When a gradient is required the reference's in-place ``u *= u_scale`` on a ``chunk`` view is
+    exactly what torch >= 2 refuses to differentiate; there the AUTOGRAD-SAFE form runs: the argument is left
+    untouched and the scaled flow is returned as a new differentiable tensor."""
     su, sv = flow_scales(flow.size(2), flow.size(3), div_flow, width_im, height_im, to_local)
+    if torch.is_grad_enabled() and flow.requires_grad:
+        return _ScaleChannels.apply(flow, su, sv)
     ops.scale_channels(flow, out=flow, s_even=su, s_odd=sv)
     return flow.clone()
 
@@ -129,10 +180,31 @@ def get_grid(x):
     return torch.cat([gx, gy], 1)
 
 
+class WarpFunction(torch.autograd.Function):
+    """WarpingLayer.forward with a hand-written backward (``irr_warp_bwd``): gradients w.r.t. the warped tensor and the
+    flow, the hard validity mask being a constant exactly as under autograd in the reference (pwc_modules.py:129-133)."""
+
+    @staticmethod
+    def forward(ctx, x, flow, height_im, width_im, div_flow):
+        x, flow = x.contiguous(), flow.contiguous()
+        ctx.save_for_backward(x, flow)
+        ctx.geom = (height_im, width_im, div_flow)
+        return ops.warp(x, flow, height_im, width_im, div_flow)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, flow = ctx.saved_tensors
+        gx, gf = ops.warp_backward(x, flow, grad_out.contiguous(), *ctx.geom, need_x=ctx.needs_input_grad[0],
+                                   need_flow=ctx.needs_input_grad[1])
+        return gx, gf, None, None, None
+
+
 class WarpingLayer(nn.Module):
-    """models/pwc_modules.py:115-133."""
+    """models/pwc_modules.py:115-133 (differentiable: ``WarpFunction`` when a gradient is required)."""
 
     def forward(self, x, flow, height_im, width_im, div_flow):
+        if torch.is_grad_enabled() and (x.requires_grad or flow.requires_grad):
+            return WarpFunction.apply(x, flow, height_im, width_im, div_flow)
         return ops.warp(x, flow, height_im, width_im, div_flow)
 
 

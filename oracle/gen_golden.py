@@ -167,6 +167,33 @@ def gen_corr_grad():
     print("corr_grad.npz", len(cases))
 
 
+def gen_warp_grad():
+    """Gradients of the reference's own WarpingLayer (pwc_modules.py:115-133) under autograd for a seeded upstream
+    gradient: d/dx and d/dflow (the hard mask is a constant for autograd).  Inputs are reproducible from the seeds; the
+    flow (built with torch ops) and the host linspace vectors are stored."""
+    cases = {}
+    wl = pwc.WarpingLayer()
+    cfgs = [((2, 5, 12, 20), 96, 160, 4.0), ((1, 16, 24, 39), 375, 1242, 6.0), ((2, 3, 28, 64), 436, 1024, 10.0)]
+    for ci, (shape, him, wim, mag) in enumerate(cfgs):
+        seed = 600 + ci
+        B, C, H, W = shape
+        x = rs_tensor(seed, shape).requires_grad_(True)
+        flow_px = rs_tensor(seed + 1000, (B, 2, H, W)) * mag
+        flow = (flow_px * 0.05 * torch.tensor([wim / W, him / H]).view(1, 2, 1, 1)).detach().requires_grad_(True)
+        go = rs_tensor(seed + 2000, shape)
+        out = wl(x, flow, him, wim, 0.05)
+        out.backward(go)
+        key = f"case{ci}"
+        cases[key + "__gx"] = x.grad.numpy()
+        cases[key + "__gflow"] = flow.grad.numpy()
+        cases[key + "__flow"] = flow.detach().numpy()
+        cases[key + "__lin_x"] = torch.linspace(-1.0, 1.0, W).numpy()
+        cases[key + "__lin_y"] = torch.linspace(-1.0, 1.0, H).numpy()
+        cases[key + "__meta"] = np.array([seed, B, C, H, W, him, wim])
+    np.savez_compressed(os.path.join(OUT, "warp_grad.npz"), **cases)
+    print("warp_grad.npz", len(cases))
+
+
 def gen_losses():
     """Eval-branch outputs of the reference's losses.py on oracle/losses_oracle.synthetic_eval_case inputs."""
     import losses as ref_losses
@@ -189,8 +216,8 @@ def gen_losses():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    if len(sys.argv) > 1 and sys.argv[1] in ("losses", "family", "corr_grad"):
-        {"losses": gen_losses, "family": gen_family, "corr_grad": gen_corr_grad}[sys.argv[1]]()
+    if len(sys.argv) > 1 and sys.argv[1] in ("losses", "family", "corr_grad", "warp_grad"):
+        {"losses": gen_losses, "family": gen_family, "corr_grad": gen_corr_grad, "warp_grad": gen_warp_grad}[sys.argv[1]]()
         sys.exit(0)
     gen_cost_volume()
     gen_warp()
@@ -198,6 +225,7 @@ if __name__ == "__main__":
     gen_models()
     gen_family()
     gen_corr_grad()
+    gen_warp_grad()
     gen_losses()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -335,6 +335,63 @@ def test_correlation_backward_golden(cuda, golden_dir, si):
         irr_b200.Correlation(20, 1, 20, 1, 2)(a, b)
 
 
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_warp_backward_golden(cuda, golden_dir, ci):
+    """irr_warp_bwd (through WarpFunction / WarpingLayer under autograd) vs the gradients of the REFERENCE's WarpingLayer
+    under autograd (tests/golden/warp_grad.npz, oracle/gen_golden.py warp_grad): d/dx and d/dflow, the hard mask a constant."""
+    from irr_b200 import ops, pwc_modules
+    g = np.load(f"{golden_dir}/warp_grad.npz")
+    seed, B, C, H, W, him, wim = (int(v) for v in g[f"case{ci}__meta"])
+    rsn = lambda sd, shp: torch.from_numpy(np.random.RandomState(sd).standard_normal(shp).astype("float32"))
+    x = rsn(seed, (B, C, H, W)).to(cuda).requires_grad_(True)
+    flow = torch.from_numpy(g[f"case{ci}__flow"]).to(cuda).requires_grad_(True)
+    go = rsn(seed + 2000, (B, C, H, W)).to(cuda)
+    out = pwc_modules.WarpingLayer()(x, flow, him, wim, 0.05)
+    assert out.grad_fn is not None
+    out.backward(go)
+    gx_ref, gf_ref = g[f"case{ci}__gx"], g[f"case{ci}__gflow"]
+    assert np.abs(x.grad.cpu().numpy() - gx_ref).max() <= 1e-5 * max(1.0, np.abs(gx_ref).max())
+    assert np.abs(flow.grad.cpu().numpy() - gf_ref).max() <= 1e-4 * max(1.0, np.abs(gf_ref).max())
+    # one-sided requests
+    gx, none = ops.warp_backward(x.detach(), flow.detach(), go, him, wim, 0.05, need_flow=False)
+    assert none is None and (gx - x.grad).abs().max().item() <= 1e-6 * max(1.0, np.abs(gx_ref).max())
+
+
+def test_autograd_safe_rescale_flow_and_conv(cuda):
+    """rescale_flow under autograd leaves its argument untouched and is differentiable (the reference's
+    in-place ``u *= scale`` on a chunk view raises on torch >= 2); conv() under autograd = our forward kernel + ATen's
+    convolution_backward on the LeakyReLU-masked gradient — both against plain torch autograd."""
+    from irr_b200 import ops, pwc_modules
+    import torch.nn.functional as F
+    fl = torch.from_numpy(rs(7, (2, 2, 9, 13))).to(cuda).requires_grad_(True)
+    before = fl.detach().clone()
+    r = pwc_modules.rescale_flow(fl, 0.05, 64, 48, to_local=False)
+    assert torch.equal(fl.detach(), before) and r.grad_fn is not None
+    su, sv = pwc_modules.flow_scales(9, 13, 0.05, 64, 48, False)
+    r.sum().backward()
+    want = torch.tensor([su, sv], device=cuda).view(1, 2, 1, 1).expand_as(fl)
+    assert (fl.grad - want).abs().max().item() <= 1e-6 * max(su, sv)
+    with torch.no_grad():   # inference keeps the reference's in-place side effect (F6)
+        t = before.clone()
+        r2 = pwc_modules.rescale_flow(t, 0.05, 64, 48, to_local=False)
+        assert torch.equal(r2, t) and not torch.equal(t, before)
+    pwc_modules.set_conv_math(ops.MATH_TC_3XF16)
+    blk = pwc_modules.conv(19, 24, kernel_size=3, stride=1, dilation=2).to(cuda)
+    x = torch.from_numpy(rs(8, (2, 19, 17, 20))).to(cuda).requires_grad_(True)
+    y = blk(x)
+    assert y.grad_fn is not None
+    go = torch.from_numpy(rs(9, tuple(y.shape))).to(cuda)
+    y.backward(go)
+    x2 = x.detach().clone().requires_grad_(True)
+    w2, b2 = blk[0].weight.detach().clone().requires_grad_(True), blk[0].bias.detach().clone().requires_grad_(True)
+    y2 = F.leaky_relu(F.conv2d(x2, w2, b2, padding=2, dilation=2), 0.1)
+    y2.backward(go)
+    assert (y - y2).abs().max().item() <= 1e-4
+    for a, b in ((x.grad, x2.grad), (blk[0].weight.grad, w2.grad), (blk[0].bias.grad, b2.grad)):
+        # a handful of outputs within 1e-6 of zero may take the other LeakyReLU branch: compare in aggregate
+        assert (a - b).abs().max().item() <= 2e-3 * max(1.0, b.abs().max().item())
+
+
 def test_round_bf16(cuda):
     """irr_round_bf16_fwd == x.bfloat16().float() bit for bit (RNE, ties, subnormals, inf, NaN), slices, in place."""
     from irr_b200 import ops
