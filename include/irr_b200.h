@@ -78,13 +78,16 @@ int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, 
                              int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
                              int f2_batch_shift, float leaky_slope, int grid_flags, irr_stream_t stream);
 
-/* The two above with an optional scratch buffer (flow == NULL: no warp, the plain cost volume).  A launch with far fewer
- * 8x32 tiles than the GPU has SMs (the 7x16 ... 14x32 pyramid levels: 16-32 tiles, up to 25 serial 8-channel chunks
- * each) deals the channel chunks of a tile to several CTAs; partial sums go to `workspace`, a second launch adds them
- * in a fixed order, scales by 1/C and applies the activation (deterministic).  workspace may be NULL (never split);
- * irr_correlation_workspace_bytes returns the size that allows every split this shape may use (0 = never split); the
- * buffer is caller-owned device memory, 16-byte aligned, private to the call until it completes on `stream`. */
-size_t irr_correlation_workspace_bytes(int B, int C, int H, int W);
+/* The two above with an optional scratch buffer (flow == NULL: no warp, the plain cost volume), used for two things:
+ *  - a launch with far fewer 8x32 tiles than the GPU has SMs (the 7x16 ... 14x32 pyramid levels: 16-32 tiles, up to 25
+ *    serial 8-channel chunks each) deals the channel chunks of a tile to several CTAs; partial sums go to the workspace,
+ *    a second launch adds them in a fixed order, scales by 1/C and applies the activation (deterministic);
+ *  - fused launches compute the bilinear taps / hard mask of every pixel ONCE in a small pre-pass (20 bytes per pixel in
+ *    the workspace) instead of per tile-halo position on the correlation kernel's compute warps.
+ * workspace may be NULL (neither happens; results are the same up to the association of the channel sum);
+ * irr_correlation_workspace_bytes(fused = 0/1) returns the size that allows both (0 = nothing to gain); the buffer is
+ * caller-owned device memory, 256-byte aligned, private to the call until it completes on `stream`. */
+size_t irr_correlation_workspace_bytes(int B, int C, int H, int W, int fused);
 int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,
                                 long long flow_bs, const float* lin_x, const float* lin_y, float* out, long long out_bs,
                                 int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,

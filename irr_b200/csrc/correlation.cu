@@ -621,13 +621,42 @@ struct TapSetup {
   }
 };
 
-template <bool FUSED, bool SPLIT>
+// Tap table pre-pass (PRETAB): one thread per pixel computes what TapSetup::setup computes per halo position — the
+// bilinear weights with the hard mask and the bounds folded in (bit-exact recipe, common.cuh) and the clamped integer
+// corner — once per PIXEL instead of once per tile-halo position (2.5x), and OFF the compute warps of the correlation
+// kernel, where it was 19 % of their time (role counters, profiles/r01_corr_role_counters.txt).  Entry: float4 weights +
+// one int  (ya << 16) | (xa << 2) | dxy  (dxy bit 0 / 1: the second column / row is a distinct in-range texel), -1 = the
+// pixel samples nothing (masked out or fully out of bounds).  Needs H < 32768 and W < 16384.
+__global__ void __launch_bounds__(256) corr_taps_kernel(const float* __restrict__ flow, long long flow_bs, GridArgs g, int H,
+                                                        int W, float4* __restrict__ tabW, int* __restrict__ tabI) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (pix >= HW) return;
+  const int b = blockIdx.y;
+  const int gy = pix / W, gx = pix - gy * W;
+  const float* fl = flow + (size_t)b * flow_bs + pix;
+  float ix, iy;
+  sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
+  const Taps tp = make_taps(ix, iy, W, H);
+  float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e = -1;
+  if (tp.mask != 0.f && (tp.w00 != 0.f || tp.w01 != 0.f || tp.w10 != 0.f || tp.w11 != 0.f)) {
+    const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
+    const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
+    e = (ya << 16) | (xa << 2) | ((xb != xa) ? 1 : 0) | ((yb != ya) ? 2 : 0);
+    w = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
+  }
+  tabW[(size_t)b * HW + pix] = w;
+  tabI[(size_t)b * HW + pix] = e;
+}
+
+template <bool FUSED, bool SPLIT, bool PRETAB>
 __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     corr_tma_kernel(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                     const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                     const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
                     GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
-                    int ntiles, int ctr, CSplit sp) {
+                    int ntiles, int ctr, CSplit sp, const float4* __restrict__ tabW, const int* __restrict__ tabI) {
   constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
   const int ksplit = SPLIT ? sp.ksplit : 1;
   const int nvt = ntiles * ksplit;
@@ -641,7 +670,8 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
   auto fpfull = [&](int s) { return bar0 + 8u * (2 * NS + s); };
   auto fpempty = [&](int s) { return bar0 + 8u * (2 * NS + T_NFS + s); };
   auto tabfull = [&](int s) { return bar0 + 8u * (2 * NS + 2 * T_NFS + s); };
-  int* meta = reinterpret_cast<int*>(bars + 2 * NS + 2 * T_NFS + 2);  // 2 x {oy, ox, foot, -}, then red[3][4]
+  auto tabempty = [&](int s) { return bar0 + 8u * (2 * NS + 2 * T_NFS + 2 + s); };   // PRETAB: samplers have read meta[s]
+  int* meta = reinterpret_cast<int*>(bars + 2 * NS + 2 * T_NFS + 4);  // 2 x {oy, ox, foot, -}, then red[3][4]
   int* red = meta + 8;
 
   const int tid = threadIdx.x;
@@ -656,15 +686,17 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       mbar_init(fpfull(s), 1);
       mbar_init(fpempty(s), T_NSAMP / 32);
     }
-    mbar_init(tabfull(0), NCOMP / 32);
-    mbar_init(tabfull(1), NCOMP / 32);
+    mbar_init(tabfull(0), PRETAB ? 1 : NCOMP / 32);
+    mbar_init(tabfull(1), PRETAB ? 1 : NCOMP / 32);
+    mbar_init(tabempty(0), T_NSAMP / 32);
+    mbar_init(tabempty(1), T_NSAMP / 32);
     for (int i = 0; i < 3; ++i) { red[4 * i] = 1 << 30; red[4 * i + 1] = -1; red[4 * i + 2] = 1 << 30; red[4 * i + 3] = -1; }
     mbar_fence_init();
   }
   __syncthreads();
 
   if (tid < NCOMP) {
-    if (FUSED) {
+    if (FUSED && !PRETAB) {
       TapSetup hook;
       hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.tiles_x = tiles_x;
       hook.tiles_y = tiles_y; hook.tab = tab; hook.meta = meta; hook.red = red; hook.tabfull0 = tabfull(0);
@@ -674,7 +706,68 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       corr_compute<NS, false, NoTileHook, SPLIT>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B,
                                                  C, H, W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
     }
-  } else if (tid == (FUSED ? T_ISSUER_FUSED : NCOMP)) {
+  } else if (FUSED && PRETAB && (tid >> 5) == (T_ISSUER_FUSED >> 5)) {
+    // ============================== COPY ISSUER, table from the pre-pass (one warp) ==============================
+    // The whole warp finds the tile's source footprint from the per-pixel tap table (20 entries per lane), lane 0
+    // publishes {oy, ox, foot} for the samplers and issues the copies.
+    const int lane = tid & 31;
+    int gchunk = 0, it = 0;
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
+      const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
+      const int c_lo = SPLIT ? ks * sp.cps : 0, c_hi = SPLIT ? min(nchunks, c_lo + sp.cps) : nchunks;
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int y0 = ty * TH, x0 = tx * TW;
+      int b2 = b + shift;
+      if (b2 >= B) b2 -= B;
+      int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
+      const int* tI = tabI + (size_t)b * HW;
+      for (int h = lane; h < NHALO; h += 32) {
+        const int hr = h / F2_WV, hx = h - hr * F2_WV;
+        const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const int e = __ldg(tI + (size_t)gy * W + gx);
+          if (e >= 0) {
+            const int ya = e >> 16, xa = (e >> 2) & 0x3fff;
+            lo_y = min(lo_y, ya); hi_y = max(hi_y, ya + ((e >> 1) & 1));
+            lo_x = min(lo_x, xa); hi_x = max(hi_x, xa + (e & 1));
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+      }
+      const bool any_live = hi_y >= lo_y;
+      const int oy = any_live ? lo_y : 0, ox = any_live ? (lo_x & ~3) : 0;   // TMA: 16-byte aligned inner coordinate
+      const int foot = (!any_live || ((hi_y - oy) < FP_H && (hi_x - ox) < FP_W)) ? 1 : 0;
+      if (lane == 0) {
+        const int slot = it & 1;
+        if (it >= 2) mbar_wait(tabempty(slot), (uint32_t)(((it >> 1) - 1) & 1));   // samplers are done with this slot
+        volatile int* mt = meta + 4 * slot;
+        mt[0] = oy; mt[1] = ox; mt[2] = foot;
+        mbar_arrive(tabfull(slot));   // release: the samplers acquire meta through their wait
+        for (int ci = c_lo; ci < c_hi; ++ci, ++gchunk) {
+          const int s = gchunk % NS;
+          mbar_wait(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1));
+          const uint32_t st = smem_u32(smem + s * STAGE_ELEMS);
+          mbar_expect_tx(full(s), T_F1_BYTES);
+          tma_load_4d(st, &m1, x0, y0, ci * CC, b, full(s));
+          const int fs = gchunk % T_NFS;
+          mbar_wait(fpempty(fs), (uint32_t)(((gchunk / T_NFS) & 1) ^ 1));
+          if (foot) {
+            mbar_expect_tx(fpfull(fs), T_FP_BYTES);
+            tma_load_4d(smem_u32(fpr + fs * FP_ELEMS), &m2, ox, oy, ci * CC, b2, fpfull(fs));
+          } else {
+            mbar_arrive(fpfull(fs));  // divergent tile: the samplers gather from global memory, keep the phases moving
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (!(FUSED && PRETAB) && tid == (FUSED ? T_ISSUER_FUSED : NCOMP)) {
     // ============================== COPY ISSUER (one thread) ==============================
     int gchunk = 0, it = 0;
     const bool con = ctr && blockIdx.x == 0;
@@ -731,13 +824,39 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       int b2 = b + shift;
       if (b2 >= B) b2 -= B;
       const float* f2b = f2 + (size_t)b2 * f2_bs;
-      // this tile's taps, from the table the compute warps filled one tile ago
+      // this tile's taps, from the table the compute warps filled one tile ago (PRETAB: from the pre-pass' table)
       const int slot = it & 1;
       mbar_wait_ctr(tabfull(slot), (uint32_t)((it >> 1) & 1), con, 16);
       const int foot = reinterpret_cast<const volatile int*>(meta)[4 * slot + 2];
       float4 wq[T_KPOS];
       int od[T_KPOS];
-      {
+      if (PRETAB) {
+        const int oy = reinterpret_cast<const volatile int*>(meta)[4 * slot], ox = reinterpret_cast<const volatile int*>(meta)[4 * slot + 1];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tabempty(slot));   // meta[slot] may be overwritten for tile it + 2
+        const int tx = tile % tiles_x;
+        const int ty = (tile / tiles_x) % tiles_y;
+        const int y0 = ty * TH, x0 = tx * TW;
+        const float4* tW = tabW + (size_t)b * HW;
+        const int* tI = tabI + (size_t)b * HW;
+#pragma unroll
+        for (int k = 0; k < T_KPOS; ++k) {
+          const int h = pt + k * T_NSAMP;
+          const int hr = h / F2_WV, hx = h - hr * F2_WV;
+          const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+          wq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          od[k] = -1;
+          if (h < NHALO && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const int e = __ldg(tI + (size_t)gy * W + gx);
+            if (e >= 0) {
+              const int ya = e >> 16, xa = (e >> 2) & 0x3fff;
+              const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * W + xa;
+              od[k] = (off << 2) | (e & 3);
+              wq[k] = __ldg(tW + (size_t)gy * W + gx);
+            }
+          }
+        }
+      } else {
         const float4* tw = reinterpret_cast<const float4*>(tab + slot * T_TAB_WORDS);
         const int* to = reinterpret_cast<const int*>(tab + slot * T_TAB_WORDS + NHALO * 4);
 #pragma unroll
@@ -886,13 +1005,25 @@ static bool corr_no_split() {  // IRR_CORR_NO_SPLIT=1: never split channels (A/B
   return e && e[0] == '1';
 }
 
-size_t corr_workspace_bytes(int B, int C, int H, int W) {
+// Workspace layout: [tap table: B*H*W float4, B*H*W int (fused launches; 256-byte aligned sections)] [split slices].
+static size_t corr_tab_bytes(int B, int H, int W) {
+  const size_t n = (size_t)B * H * W;
+  return ((n * 16 + 255) / 256) * 256 + ((n * 4 + 255) / 256) * 256;
+}
+static bool corr_no_pretab() {  // IRR_CORR_NO_PRETAB=1: tap set-up inside the correlation kernel (A/B measurements)
+  const char* e = getenv("IRR_CORR_NO_PRETAB");
+  return e && e[0] == '1';
+}
+
+size_t corr_workspace_bytes(int B, int C, int H, int W, int fused) {
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   const long long nt = (long long)tiles_x * tiles_y * B;
   if (nt > 0x7fffffffLL) return 0;
   int cps;
   const int k = corr_ksplit((int)nt, (C + CC - 1) / CC, &cps);
-  return k > 1 ? (size_t)k * B * (ND * ND) * H * W * sizeof(float) : 0;
+  size_t n = k > 1 ? (size_t)k * B * (ND * ND) * H * W * sizeof(float) : 0;
+  if (fused && H < 32768 && W < 16384) n += corr_tab_bytes(B, H, W);
+  return n;
 }
 
 static bool corr_no_tma() {  // IRR_CORR_NO_TMA=1: force the cp.async kernel (A/B measurements, tests of the fallback)
@@ -925,7 +1056,7 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
   if (vec_in && !corr_no_tma()) {
     constexpr int TSMEM = FUSED ? CORR_SMEM_TMA_FUSED : CORR_SMEM_TMA_PLAIN;
-    static SmemAttrCache tattr = {}, tattr_split = {};
+    static SmemAttrCache tattr = {}, tattr_split = {}, tattr_pre = {}, tattr_pre_split = {};
     CUtensorMap m1, m2;
     if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC) &&
         make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC)) {
@@ -935,27 +1066,48 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
         cudaMemcpyToSymbolAsync(corr_ctr, zeros, sizeof(zeros), 0, cudaMemcpyHostToDevice, st);
       }
       CSplit sp = {1, 0, nullptr, 0};
-      if (ws != nullptr && !corr_no_split() && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+      uint8_t* wsp = reinterpret_cast<uint8_t*>(ws);
+      size_t ws_left = ws_bytes;
+      float4* tabW = nullptr;
+      int* tabI = nullptr;
+      // tap table from a pre-pass (fused launches): the table goes first in the workspace
+      if (FUSED && wsp != nullptr && (reinterpret_cast<uintptr_t>(wsp) & 255) == 0 && !corr_no_pretab() && !ctr && H < 32768 &&
+          W < 16384 && corr_tab_bytes(B, H, W) <= ws_left) {
+        const size_t n = (size_t)B * H * W;
+        tabW = reinterpret_cast<float4*>(wsp);
+        tabI = reinterpret_cast<int*>(wsp + ((n * 16 + 255) / 256) * 256);
+        wsp += corr_tab_bytes(B, H, W);
+        ws_left -= corr_tab_bytes(B, H, W);
+        dim3 pg((unsigned)((H * W + 255) / 256), (unsigned)B);
+        corr_taps_kernel<<<pg, 256, 0, st>>>(flow, flow_bs, g, H, W, tabW, tabI);
+        if (int rc = check_launch(fn)) return rc;
+      }
+      if (wsp != nullptr && !corr_no_split() && (reinterpret_cast<uintptr_t>(wsp) & 15) == 0) {
         int cps;
         const int k = corr_ksplit(ntiles, (C + CC - 1) / CC, &cps);
         const size_t slice = (size_t)B * (ND * ND) * H * W;
-        if (k > 1 && (size_t)k * slice * sizeof(float) <= ws_bytes) {
-          sp.ksplit = k; sp.cps = cps; sp.ws = reinterpret_cast<float*>(ws); sp.ws_stride = (long long)slice;
+        if (k > 1 && (size_t)k * slice * sizeof(float) <= ws_left) {
+          sp.ksplit = k; sp.cps = cps; sp.ws = reinterpret_cast<float*>(wsp); sp.ws_stride = (long long)slice;
           const long long nvt = (long long)ntiles * k;
           grid = nvt < sm_count() ? (int)nvt : sm_count();
         }
       }
-      if (sp.ksplit > 1) {
-        if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, true>, TSMEM, tattr_split, fn)) return rc;
-        corr_tma_kernel<FUSED, true><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(
-            m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,
-            ntiles, ctr, sp);
+      const int nthr = FUSED ? CORR_THREADS : T_PLAIN_THREADS;
+#define IRR_CORR_LAUNCH(SPLIT_, PRE_, CACHE_)                                                                              \
+  do {                                                                                                                     \
+    if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, SPLIT_, PRE_>, TSMEM, CACHE_, fn)) return rc;                       \
+    corr_tma_kernel<FUSED, SPLIT_, PRE_><<<grid, nthr, TSMEM, st>>>(m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, \
+                                                                   g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,  \
+                                                                   ntiles, ctr, sp, tabW, tabI);                           \
+  } while (0)
+      if (FUSED && tabW != nullptr) {
+        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, FUSED, tattr_pre_split);
+        else IRR_CORR_LAUNCH(false, FUSED, tattr_pre);
       } else {
-        if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, false>, TSMEM, tattr, fn)) return rc;
-        corr_tma_kernel<FUSED, false><<<grid, FUSED ? CORR_THREADS : T_PLAIN_THREADS, TSMEM, st>>>(
-            m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,
-            ntiles, ctr, sp);
+        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, false, tattr_split);
+        else IRR_CORR_LAUNCH(false, false, tattr);
       }
+#undef IRR_CORR_LAUNCH
       if (int rc = check_launch(fn)) return rc;
       if (sp.ksplit > 1) {
         const long long total = (long long)B * (ND * ND) * H * W;
@@ -990,9 +1142,9 @@ int irr_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long 
                             leaky_slope, nullptr, 0, as_stream(stream));
 }
 
-size_t irr_correlation_workspace_bytes(int B, int C, int H, int W) {
+size_t irr_correlation_workspace_bytes(int B, int C, int H, int W, int fused) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-  return corr_workspace_bytes(B, C, H, W);
+  return corr_workspace_bytes(B, C, H, W, fused);
 }
 
 int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,

@@ -107,12 +107,13 @@ def _new(like: torch.Tensor, C: int, H: int, W: int) -> torch.Tensor:
 _corr_ws_bytes = {}
 
 
-def _corr_workspace(B, C, H, W, device):
-    """Scratch for the channel-split plan of coarse-level cost volumes (0 bytes = this shape is never split)."""
-    key = (B, C, H, W)
+def _corr_workspace(B, C, H, W, device, fused=False):
+    """Scratch for the channel-split plan of coarse-level cost volumes and, for fused launches, the per-pixel tap table
+    of the pre-pass (0 bytes = neither applies to this shape)."""
+    key = (B, C, H, W, bool(fused))
     n = _corr_ws_bytes.get(key)
     if n is None:
-        n = _lib.load().irr_correlation_workspace_bytes(B, C, H, W)
+        n = _lib.load().irr_correlation_workspace_bytes(B, C, H, W, 1 if fused else 0)
         _corr_ws_bytes[key] = n
     return (torch.empty(n // 4, dtype=torch.float32, device=device), n) if n else (None, 0)
 
@@ -145,7 +146,7 @@ def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: floa
     lx = host_linspace(W, f1.device) if lin_x is None else lin_x
     ly = host_linspace(H, f1.device) if lin_y is None else lin_y
     p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
-    ws, nws = _corr_workspace(B, C, H, W, f1.device)
+    ws, nws = _corr_workspace(B, C, H, W, f1.device, fused=True)
     _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, pf, sf,
             _p(lx, "lin_x", f1, W), _p(ly, "lin_y", f1, H), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp,
             shift, slope, _grid_mode, ws.data_ptr() if ws is not None else None, nws, _stream())

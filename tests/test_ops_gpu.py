@@ -202,6 +202,16 @@ def test_cost_volume_full_size_properties(cuda):
     for (y, x, dy, dx) in [(0, 0, -4, -4), (0, 255, 4, 4), (108, 0, 4, -4), (54, 128, 1, -2), (108, 255, -3, 0), (7, 31, 0, 4)]:
         want = (f1[:, :, y, x] * f2p[:, :, y + dy + 4, x + dx + 4]).sum(1) / C
         assert (a[:, (dy + 4) * 9 + (dx + 4), y, x] - want).abs().max().item() <= 1e-5
+    # the tap table of the pre-pass gives bit-identical results to the in-kernel tap set-up (same recipe, same order)
+    fused_pre = ops.warp_correlation(f1, f2, smooth, 436, 1024, 0.05, shift=B // 2, slope=0.1)
+    os.environ["IRR_CORR_NO_PRETAB"] = "1"
+    try:
+        assert torch.equal(ops.warp_correlation(f1, f2, smooth, 436, 1024, 0.05, shift=B // 2, slope=0.1), fused_pre)
+    finally:
+        del os.environ["IRR_CORR_NO_PRETAB"]
+    wild = torch.randn(B, 2, H, W, generator=g).to(cuda) * 3.0      # divergent flow: tiles fall back to global gathers
+    fw = ops.warp_correlation(f1, f2, wild, 436, 1024, 0.05, shift=B // 2)
+    assert (fw - ops.correlation(f1, ops.warp(f2, wild, 436, 1024, 0.05, shift=B // 2))).abs().max().item() <= 1e-6
     # the cp.async fallback kernel computes the same sums in the same order
     os.environ["IRR_CORR_NO_TMA"] = "1"
     try:
@@ -221,7 +231,7 @@ def test_cost_volume_channel_split(cuda, shape):
     f1 = dev(rs(41, (B, C, H, W)), cuda)
     f2 = dev(rs(42, (B, C, H, W)), cuda)
     flow = dev(rs(43, (B, 2, H, W)), cuda) * 0.3
-    nws = _lib.load().irr_correlation_workspace_bytes(B, C, H, W)
+    nws = _lib.load().irr_correlation_workspace_bytes(B, C, H, W, 0)
     if shape[0] * ((H + 7) // 8) * ((W + 31) // 32) * 2 <= 148 and C > 8:
         assert nws > 0      # these launches are split on a 148-SM part
     a = ops.correlation(f1, f2, shift=B // 2, slope=0.1)
