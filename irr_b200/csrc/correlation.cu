@@ -26,17 +26,33 @@
 
 #include "common.cuh"
 
-namespace irr {
+// This file is compiled twice: as is (8-row tiles, every entry point) and from correlation7.cu with IRR_CORR_TH = 7
+// (namespace irr::corr7, only launch_corr<true> is used).  With 7-row tiles the 63 (row, displacement-row) pairs of a tile
+// make exactly 8 compute warps — two per scheduler — where the 72 pairs of an 8-row tile make 9, which load the four
+// schedulers 3:2:2:2 and leave the kernel waiting on scheduler 0.
+#ifndef IRR_CORR_TH
+#define IRR_CORR_TH 8
+#endif
+#if IRR_CORR_TH == 8
+#define IRR_CORR_NS corr8
+#else
+#define IRR_CORR_NS corr7
+#define IRR_CORR_VARIANT_ONLY 1
+#endif
 
-constexpr int TH = 8, TW = 32, MD = 4, ND = 9, PX = 8;
+namespace irr {
+namespace IRR_CORR_NS {
+
+constexpr int TH = IRR_CORR_TH, TW = 32, MD = 4, ND = 9, PX = 8;
 constexpr int F1_P = 36;                    // f1 row pitch (floats)
-constexpr int F2_H = TH + 2 * MD;           // 16
+constexpr int F2_H = TH + 2 * MD;           // 16 (15)
 constexpr int F2_WV = TW + 2 * MD;          // 40 valid halo columns
 constexpr int F2_P = 44;                    // f2 row pitch (floats)
 constexpr int CC = 8;                       // channels per chunk
-constexpr int NCOMP = 32 * ND;              // 288 compute threads
+constexpr int NPAIR = TH * ND;              // (tile row, displacement row) pairs: 72 (63)
+constexpr int NCOMP = ((NPAIR * (TW / PX) + 31) / 32) * 32;   // compute threads: 288 = 9 warps (256 = 8 warps)
 constexpr int NPROD = 224;                  // 7 producer warps
-constexpr int CORR_THREADS = NCOMP + NPROD; // 512
+constexpr int CORR_THREADS = NCOMP + NPROD; // 512 (480)
 constexpr int CORR_STAGES = 3;
 constexpr int F1_ELEMS = CC * TH * F1_P;    // 2304
 constexpr int F2_ELEMS = CC * F2_H * F2_P;  // 5632
@@ -116,15 +132,20 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
   const int lane = tid & 31;
   const int s8 = lane & 3;
   int r, dyi;
+  bool pair_ok;
   {
-    int p = (tid >> 5) * 8 + (lane >> 2), h = 0;  // p-th pair in (h, r) order; row h holds min(h, 15 - h) + 1 pairs
+    // p-th pair in (h, r) order; halo row h holds min(h, TH-1, ND-1, TH+ND-2-h) + 1 pairs.  A 7-row tile has 63 pairs:
+    // the last four lanes of warp 7 shadow pair 0 (their loads stay in bounds, they store nothing).
+    int p = (tid >> 5) * 8 + (lane >> 2), h = 0;
+    pair_ok = p < NPAIR;
+    if (!pair_ok) p = 0;
     for (;;) {
-      const int cnt = (h < 8 ? h : 15 - h) + 1;
+      const int cnt = min(min(h, TH - 1), min(ND - 1, TH + ND - 2 - h)) + 1;
       if (p < cnt) break;
       p -= cnt;
       ++h;
     }
-    r = (h > 8 ? h - 8 : 0) + p;
+    r = max(h - (ND - 1), 0) + p;
     dyi = h - r;  // 0..8 -> dy = dyi - 4
   }
   int gchunk = 0, it = 0;
@@ -207,7 +228,7 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     const int gx = x0 + s8 * PX;
     if (SPLIT) {
       // channel-split launch: raw partial sums of chunks [c_lo, c_hi) into this split's workspace slice
-      if (gy < H && gx < W) {
+      if (pair_ok && gy < H && gx < W) {
         float* op = sp.ws + (size_t)ks * sp.ws_stride + ((size_t)b * (ND * ND) + (size_t)(dyi * ND)) * HW + (size_t)gy * W + gx;
         if ((W & 3) == 0 && gx + PX <= W) {
 #pragma unroll
@@ -224,7 +245,7 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
               if (gx + p < W) op[(size_t)d * HW + p] = acc[d][p];
         }
       }
-    } else if (gy < H && gx < W) {
+    } else if (pair_ok && gy < H && gx < W) {
       const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
       float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
       // scale in place first, then issue the stores back to back (a temporary per displacement makes every store
@@ -708,10 +729,58 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     }
   } else if (FUSED && PRETAB && (tid >> 5) == (T_ISSUER_FUSED >> 5)) {
     // ============================== COPY ISSUER, table from the pre-pass (one warp) ==============================
-    // The whole warp finds the tile's source footprint from the per-pixel tap table (20 entries per lane), lane 0
-    // publishes {oy, ox, foot} for the samplers and issues the copies.
+    // The whole warp finds a tile's source footprint from the per-pixel tap table (20 entries per lane), ONE TILE AHEAD
+    // (the loads of tile t+1 are in flight while lane 0 issues the copies of tile t); lane 0 publishes {oy, ox, foot}
+    // for the samplers and issues the copies.
     const int lane = tid & 31;
     int gchunk = 0, it = 0;
+    // footprint of virtual tile vt -> (oy, ox, foot), identical in every lane
+    auto footprint = [&](int vt, int& oy, int& ox, int& foot) {
+      const int tile = SPLIT ? vt / ksplit : vt;
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int y0 = ty * TH, x0 = tx * TW;
+      int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
+      const int* tI = tabI + (size_t)b * HW;
+      int e[(NHALO + 31) / 32];
+#pragma unroll
+      for (int k = 0; k < (NHALO + 31) / 32; ++k) {   // all loads in flight first
+        const int h = lane + 32 * k;
+        const int hr = h / F2_WV, hx = h - hr * F2_WV;
+        const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+        e[k] = (h < NHALO && gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(tI + (size_t)gy * W + gx) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < (NHALO + 31) / 32; ++k) {
+        if (e[k] >= 0) {
+          const int ya = e[k] >> 16, xa = (e[k] >> 2) & 0x3fff;
+          lo_y = min(lo_y, ya); hi_y = max(hi_y, ya + ((e[k] >> 1) & 1));
+          lo_x = min(lo_x, xa); hi_x = max(hi_x, xa + (e[k] & 1));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+      }
+      const bool any_live = hi_y >= lo_y;
+      oy = any_live ? lo_y : 0;
+      ox = any_live ? (lo_x & ~3) : 0;   // TMA: 16-byte aligned inner coordinate
+      foot = (!any_live || ((hi_y - oy) < FP_H && (hi_x - ox) < FP_W)) ? 1 : 0;
+    };
+    auto publish = [&](int j, int oy, int ox, int foot) {   // lane 0: meta of the j-th tile of this CTA
+      const int slot = j & 1;
+      if (j >= 2) mbar_wait(tabempty(slot), (uint32_t)(((j >> 1) - 1) & 1));   // samplers are done with this slot
+      volatile int* mt = meta + 4 * slot;
+      mt[0] = oy; mt[1] = ox; mt[2] = foot;
+      mbar_arrive(tabfull(slot));   // release: the samplers acquire meta through their wait
+    };
+    int oy = 0, ox = 0, foot = 1;
+    if ((int)blockIdx.x < nvt) {
+      footprint(blockIdx.x, oy, ox, foot);
+      if (lane == 0) publish(0, oy, ox, foot);
+    }
     for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
       const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
       const int c_lo = SPLIT ? ks * sp.cps : 0, c_hi = SPLIT ? min(nchunks, c_lo + sp.cps) : nchunks;
@@ -721,34 +790,11 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       const int y0 = ty * TH, x0 = tx * TW;
       int b2 = b + shift;
       if (b2 >= B) b2 -= B;
-      int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
-      const int* tI = tabI + (size_t)b * HW;
-      for (int h = lane; h < NHALO; h += 32) {
-        const int hr = h / F2_WV, hx = h - hr * F2_WV;
-        const int gy = y0 - MD + hr, gx = x0 - MD + hx;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-          const int e = __ldg(tI + (size_t)gy * W + gx);
-          if (e >= 0) {
-            const int ya = e >> 16, xa = (e >> 2) & 0x3fff;
-            lo_y = min(lo_y, ya); hi_y = max(hi_y, ya + ((e >> 1) & 1));
-            lo_x = min(lo_x, xa); hi_x = max(hi_x, xa + (e & 1));
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
-        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
-      }
-      const bool any_live = hi_y >= lo_y;
-      const int oy = any_live ? lo_y : 0, ox = any_live ? (lo_x & ~3) : 0;   // TMA: 16-byte aligned inner coordinate
-      const int foot = (!any_live || ((hi_y - oy) < FP_H && (hi_x - ox) < FP_W)) ? 1 : 0;
+      int noy = 0, nox = 0, nfoot = 1;
+      const bool has_next = vt + (int)gridDim.x < nvt;
+      if (has_next) footprint(vt + (int)gridDim.x, noy, nox, nfoot);
       if (lane == 0) {
-        const int slot = it & 1;
-        if (it >= 2) mbar_wait(tabempty(slot), (uint32_t)(((it >> 1) - 1) & 1));   // samplers are done with this slot
-        volatile int* mt = meta + 4 * slot;
-        mt[0] = oy; mt[1] = ox; mt[2] = foot;
-        mbar_arrive(tabfull(slot));   // release: the samplers acquire meta through their wait
+        if (has_next) publish(it + 1, noy, nox, nfoot);
         for (int ci = c_lo; ci < c_hi; ++ci, ++gchunk) {
           const int s = gchunk % NS;
           mbar_wait(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1));
@@ -766,6 +812,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         }
       }
       __syncwarp();
+      oy = noy; ox = nox; foot = nfoot;
     }
   } else if (!(FUSED && PRETAB) && tid == (FUSED ? T_ISSUER_FUSED : NCOMP)) {
     // ============================== COPY ISSUER (one thread) ==============================
@@ -817,6 +864,28 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     int gchunk = 0, it = 0;
     const bool con = ctr && blockIdx.x == 0 && pt == 0;
     const long long ct0 = con ? clock64() : 0;
+    // PRETAB: this thread's raw table entries of the NEXT tile (loaded while the current tile is sampled)
+    int pre_e[T_KPOS];
+    float4 pre_w[T_KPOS];
+    auto load_entries = [&](int vtile) {
+      const int tl = SPLIT ? vtile / ksplit : vtile;
+      const int tx = tl % tiles_x;
+      const int ty = (tl / tiles_x) % tiles_y;
+      const int tb = tl / (tiles_x * tiles_y);
+      const int y0 = ty * TH, x0 = tx * TW;
+      const float4* tW = tabW + (size_t)tb * HW;
+      const int* tI = tabI + (size_t)tb * HW;
+#pragma unroll
+      for (int k = 0; k < T_KPOS; ++k) {
+        const int h = pt + k * T_NSAMP;
+        const int hr = h / F2_WV, hx = h - hr * F2_WV;
+        const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+        const bool in = h < NHALO && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        pre_e[k] = in ? __ldg(tI + (size_t)gy * W + gx) : -1;
+        pre_w[k] = in ? __ldg(tW + (size_t)gy * W + gx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (PRETAB && (int)blockIdx.x < nvt) load_entries(blockIdx.x);
     for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
       const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
       const int c_lo = SPLIT ? ks * sp.cps : 0, c_hi = SPLIT ? min(nchunks, c_lo + sp.cps) : nchunks;
@@ -834,28 +903,18 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         const int oy = reinterpret_cast<const volatile int*>(meta)[4 * slot], ox = reinterpret_cast<const volatile int*>(meta)[4 * slot + 1];
         __syncwarp();
         if (lane == 0) mbar_arrive(tabempty(slot));   // meta[slot] may be overwritten for tile it + 2
-        const int tx = tile % tiles_x;
-        const int ty = (tile / tiles_x) % tiles_y;
-        const int y0 = ty * TH, x0 = tx * TW;
-        const float4* tW = tabW + (size_t)b * HW;
-        const int* tI = tabI + (size_t)b * HW;
 #pragma unroll
-        for (int k = 0; k < T_KPOS; ++k) {
-          const int h = pt + k * T_NSAMP;
-          const int hr = h / F2_WV, hx = h - hr * F2_WV;
-          const int gy = y0 - MD + hr, gx = x0 - MD + hx;
+        for (int k = 0; k < T_KPOS; ++k) {   // entries were loaded one tile ago (pre_e / pre_w)
           wq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           od[k] = -1;
-          if (h < NHALO && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const int e = __ldg(tI + (size_t)gy * W + gx);
-            if (e >= 0) {
-              const int ya = e >> 16, xa = (e >> 2) & 0x3fff;
-              const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * W + xa;
-              od[k] = (off << 2) | (e & 3);
-              wq[k] = __ldg(tW + (size_t)gy * W + gx);
-            }
+          if (pre_e[k] >= 0) {
+            const int ya = pre_e[k] >> 16, xa = (pre_e[k] >> 2) & 0x3fff;
+            const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * W + xa;
+            od[k] = (off << 2) | (pre_e[k] & 3);
+            wq[k] = pre_w[k];
           }
         }
+        if (vt + (int)gridDim.x < nvt) load_entries(vt + (int)gridDim.x);   // next tile's entries, in flight during this tile
       } else {
         const float4* tw = reinterpret_cast<const float4*>(tab + slot * T_TAB_WORDS);
         const int* to = reinterpret_cast<const int*>(tab + slot * T_TAB_WORDS + NHALO * 4);
@@ -1123,9 +1182,33 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   return check_launch(fn);
 }
 
+// The fused launcher under a plain name, so the other translation unit (7-row tiles) can be called from this one.
+int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
+                              const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
+                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, ws, ws_bytes, st);
+}
+
+}  // namespace IRR_CORR_NS
+}  // namespace irr
+
+#ifndef IRR_CORR_VARIANT_ONLY
+namespace irr {
+namespace corr7 {
+int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
+                              const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
+                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t corr_workspace_bytes(int B, int C, int H, int W, int fused);
+}  // namespace corr7
 }  // namespace irr
 
 using namespace irr;
+using namespace irr::corr8;
+
+static bool corr_force_th8() {  // IRR_CORR_TH8=1: keep fused launches on the 8-row-tile kernel (A/B measurements)
+  const char* e = getenv("IRR_CORR_TH8");
+  return e && e[0] == '1';
+}
 
 extern "C" {
 
@@ -1144,7 +1227,9 @@ int irr_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long 
 
 size_t irr_correlation_workspace_bytes(int B, int C, int H, int W, int fused) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-  return corr_workspace_bytes(B, C, H, W, fused);
+  const size_t a = corr8::corr_workspace_bytes(B, C, H, W, fused);
+  const size_t b = fused ? corr7::corr_workspace_bytes(B, C, H, W, fused) : 0;   // fused launches use 7-row tiles
+  return a > b ? a : b;
 }
 
 int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,
@@ -1164,6 +1249,9 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
   }
   IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
+  if (workspace != nullptr && !corr_force_th8())   // 7-row tiles: 8 compute warps, two per scheduler (correlation7.cu)
+    return corr7::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
+                                            f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));
   return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
                            workspace, workspace_bytes, as_stream(stream));
 }
@@ -1228,3 +1316,4 @@ int irr_correlation_generic_fwd(const float* in1, const float* in2, float* out, 
 }
 
 }  // extern "C"
+#endif  // IRR_CORR_VARIANT_ONLY
