@@ -676,7 +676,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
 // 12-15 epilogue.
 constexpr int R_THREADS = 512;
 constexpr int R_XS = 6;          // staged input rows in flight
-constexpr int R_SA = 8;          // A ring stages in TMEM (32 columns each) at column 256
+constexpr int R_SR = 4;          // A ring in TMEM: row stages of 3 x 32 columns (the kx = 0, 1, 2 views of one input row)
+constexpr int R_ACOL = 128;      // ... starting at column 128 (accumulators: 4 output-row slots x 32 columns in [0, 128))
+constexpr int R_ACC = 32;        // accumulator slot stride (n_tile <= 32)
 constexpr int R_PW = 136;        // staged row width: 4 (aligned left halo) + 128 + 1 (+3 pad)
 constexpr int R_XBYTES = H_CK * R_PW * 4;
 
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
   if (tid < 64) bias_s[tid] = tid < p.Cout ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
     for (int s = 0; s < R_XS; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 4); }  // 4 warps of the owning group
-    for (int s = 0; s < R_SA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 3); }
+    for (int s = 0; s < R_SR; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 3); }
     for (int s = 0; s < 4; ++s) { mbar_init(acc_full(s), 3); mbar_init(acc_empty(s), 4); }
     for (int s = 0; s < 8; ++s) mbar_init(ord(s >> 2, s & 3), 1);
     mbar_init(w_full, 1);
@@ -799,29 +801,33 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         H_ACC(1);
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + pt + 3;  // column of tap kx = 0 (4 - pad)
+        // One A stage per input ROW: its three kx-shifted views go to three 32-column blocks of row stage cx % R_SR and
+        // are handed to the issuers with ONE arrive (per-tap stages cost three producer->issuer->producer round trips
+        // per row, and the kernel's row time did not depend on the MMA count — it was those hand-offs).
+        const int sr = cx % R_SR;
+        const uint32_t a_row = lane_addr + (uint32_t)(R_ACOL + sr * 96);
 #pragma unroll 1
         for (int kx = 0; kx < 3; ++kx) {
-          const int ca = 3 * cx + kx;
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             hi[k] = xw[(2 * k) * R_PW + kx];
             lo[k] = xw[(2 * k + 1) * R_PW + kx];
           }
-          const int sa = ca % R_SA;
           H_ACC(2);
-          mbar_wait(a_empty(sa), (uint32_t)(((ca / R_SA) & 1) ^ 1));
-          h_fence_after();
+          if (kx == 0) {
+            mbar_wait(a_empty(sr), (uint32_t)(((cx / R_SR) & 1) ^ 1));
+            h_fence_after();
+          }
           H_ACC(3);
-          const uint32_t a_addr = lane_addr + (uint32_t)(H_A_COL + sa * 32);
-          h_tmem_st16(a_addr, hi);
-          h_tmem_st16(a_addr + 16, lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          h_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(a_full(sa));
-          H_ACC(4);
+          h_tmem_st16(a_row + (uint32_t)(kx * 32), hi);
+          h_tmem_st16(a_row + (uint32_t)(kx * 32 + 16), lo);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        h_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(sr));
+        H_ACC(4);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(x_empty(sx));
@@ -836,35 +842,35 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const bool two = p.Cin > 16;
     mbar_wait(w_full, 0);
-    int ca = 0, obase = 0;
+    int cx = 0, obase = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, ya, nr, x0;
       item_decode(item, b, ya, nr, x0);
-      for (int i = 0; i < nr + 2; ++i) {
+      for (int i = 0; i < nr + 2; ++i, ++cx) {
         const int oi = i - ky;                 // output row (inside the segment) this input row feeds through tap ky
         const bool valid = oi >= 0 && oi < nr;
         const int og = obase + oi;             // running output-row counter -> accumulator slot and phase
         const int slot = og & 3;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 64);
-#pragma unroll 1
-        for (int kx = 0; kx < 3; ++kx, ++ca) {
-          const int sa = ca % R_SA;
-          H_T0();
-          mbar_wait(a_full(sa), (uint32_t)((ca / R_SA) & 1));
-          H_ACC(0);
-          if (valid && kx == 0) {
-            mbar_wait(acc_empty(slot), (uint32_t)((og >> 2) & 1));  // drained and zeroed
-            // bit-determinism: the ky = 0 group of this output row (issued one staged row earlier by warp 8) must have
-            // been accumulated before ky = 1 adds to it, and ky = 1 before ky = 2.  The predecessor finished a whole
-            // producer row (~1600 clk) ago in steady state, so this wait is almost always already satisfied.
-            if (ky > 0 && !p.unordered) mbar_wait(ord(ky - 1, slot), (uint32_t)((og >> 2) & 1));
-          }
-          h_fence_after();
-          H_ACC(1);
-          if (h_elect()) {
-            if (valid) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * R_ACC);
+        const int sr = cx % R_SR;
+        H_T0();
+        mbar_wait(a_full(sr), (uint32_t)((cx / R_SR) & 1));
+        H_ACC(0);
+        if (valid) {
+          mbar_wait(acc_empty(slot), (uint32_t)((og >> 2) & 1));  // drained and zeroed
+          // bit-determinism: the ky = 0 group of this output row (issued one staged row earlier by warp 8) must have
+          // been accumulated before ky = 1 adds to it, and ky = 1 before ky = 2.  The predecessor finished a whole
+          // producer row ago in steady state, so this wait is almost always already satisfied.
+          if (ky > 0 && !p.unordered) mbar_wait(ord(ky - 1, slot), (uint32_t)((og >> 2) & 1));
+        }
+        h_fence_after();
+        H_ACC(1);
+        if (h_elect()) {
+          if (valid) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
               const uint64_t bd = h_b_desc(smem_u32(smem_w) + (uint32_t)(ky * 3 + kx) * img_bytes);
-              const uint32_t a_hi = tmem_base + (uint32_t)(H_A_COL + sa * 32);
+              const uint32_t a_hi = tmem_base + (uint32_t)(R_ACOL + sr * 96 + kx * 32);
               h_mma_ts(d_tmem, a_hi + 16, bd, idesc, 1u);   // lo * hi
               h_mma_ts(d_tmem, a_hi, bd + 4, idesc, 1u);    // hi * lo
               h_mma_ts(d_tmem, a_hi, bd, idesc, 1u);        // hi * hi
@@ -873,19 +879,17 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                 h_mma_ts(d_tmem, a_hi + 8, bd + 6, idesc, 1u);
                 h_mma_ts(d_tmem, a_hi + 8, bd + 2, idesc, 1u);
               }
-              h_commit(a_empty(sa));
-              if (kx == 2) {
-                if (ky < 2) h_commit(ord(ky, slot));
-                h_commit(acc_full(slot));
-              }
-            } else {
-              mbar_arrive(a_empty(sa));
             }
+            h_commit(a_empty(sr));
+            if (ky < 2) h_commit(ord(ky, slot));
+            h_commit(acc_full(slot));
+          } else {
+            mbar_arrive(a_empty(sr));
           }
-          __syncwarp();
-          H_ACC(2);
-          if (CTR) cacc[5] += 1;
         }
+        __syncwarp();
+        H_ACC(2);
+        if (CTR) cacc[5] += 3;
       }
       obase += nr;
     }
@@ -924,7 +928,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     uint32_t zero[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) zero[j] = 0u;
-    for (int c0 = 0; c0 < 256; c0 += 16) h_tmem_st16(lane_addr + (uint32_t)c0, zero);
+    for (int c0 = 0; c0 < 4 * R_ACC; c0 += 16) h_tmem_st16(lane_addr + (uint32_t)c0, zero);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     h_fence_before();
     __syncwarp();
@@ -972,7 +976,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         mbar_wait(acc_full(slot), (uint32_t)((og >> 2) & 1));
         h_fence_after();
         H_ACC(0);
-        const uint32_t acc_addr = lane_addr + (uint32_t)(slot * 64);
+        const uint32_t acc_addr = lane_addr + (uint32_t)(slot * R_ACC);
         uint32_t r[NG * 16];
 #pragma unroll
         for (int g = 0; g < NG; ++g) h_tmem_ld16(acc_addr + (uint32_t)(g * 16), r + g * 16);

@@ -1069,9 +1069,12 @@ static size_t corr_tab_bytes(int B, int H, int W) {
   const size_t n = (size_t)B * H * W;
   return ((n * 16 + 255) / 256) * 256 + ((n * 4 + 255) / 256) * 256;
 }
-static bool corr_no_pretab() {  // IRR_CORR_NO_PRETAB=1: tap set-up inside the correlation kernel (A/B measurements)
-  const char* e = getenv("IRR_CORR_NO_PRETAB");
-  return e && e[0] == '1';
+// The pre-pass variant is OFF by default: measured on the B200 (profiles/r02_bench_corr_variants.txt) it is SLOWER than
+// the in-kernel set-up (level 4 fused: 188 us vs 143 us) — the compute warps are not the critical path of the fused
+// kernel, the sampler / copy chain is, and the table look-ups lengthen it.  IRR_CORR_PRETAB=1 enables it (A/B runs, tests).
+static bool corr_no_pretab() {
+  const char* e = getenv("IRR_CORR_PRETAB");
+  return !(e && e[0] == '1');
 }
 
 size_t corr_workspace_bytes(int B, int C, int H, int W, int fused) {
@@ -1081,7 +1084,7 @@ size_t corr_workspace_bytes(int B, int C, int H, int W, int fused) {
   int cps;
   const int k = corr_ksplit((int)nt, (C + CC - 1) / CC, &cps);
   size_t n = k > 1 ? (size_t)k * B * (ND * ND) * H * W * sizeof(float) : 0;
-  if (fused && H < 32768 && W < 16384) n += corr_tab_bytes(B, H, W);
+  if (fused && !corr_no_pretab() && H < 32768 && W < 16384) n += corr_tab_bytes(B, H, W);
   return n;
 }
 
@@ -1205,9 +1208,11 @@ size_t corr_workspace_bytes(int B, int C, int H, int W, int fused);
 using namespace irr;
 using namespace irr::corr8;
 
-static bool corr_force_th8() {  // IRR_CORR_TH8=1: keep fused launches on the 8-row-tile kernel (A/B measurements)
-  const char* e = getenv("IRR_CORR_TH8");
-  return e && e[0] == '1';
+// The 7-row-tile variant is OFF by default: measured on the B200 it is slower than 8-row tiles (level 4 fused: 171 us vs
+// 143 us — 14 % more tiles and 7 % more halo per pixel outweigh the balanced schedulers).  IRR_CORR_TH7=1 selects it.
+static bool corr_force_th8() {
+  const char* e = getenv("IRR_CORR_TH7");
+  return !(e && e[0] == '1');
 }
 
 extern "C" {
@@ -1249,7 +1254,7 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
   }
   IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
-  if (workspace != nullptr && !corr_force_th8())   // 7-row tiles: 8 compute warps, two per scheduler (correlation7.cu)
+  if (!corr_force_th8())   // experimental: 7-row tiles, 8 compute warps, two per scheduler (correlation7.cu)
     return corr7::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
                                             f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));
   return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,

@@ -203,12 +203,19 @@ def test_cost_volume_full_size_properties(cuda):
         want = (f1[:, :, y, x] * f2p[:, :, y + dy + 4, x + dx + 4]).sum(1) / C
         assert (a[:, (dy + 4) * 9 + (dx + 4), y, x] - want).abs().max().item() <= 1e-5
     # the tap table of the pre-pass gives bit-identical results to the in-kernel tap set-up (same recipe, same order)
-    fused_pre = ops.warp_correlation(f1, f2, smooth, 436, 1024, 0.05, shift=B // 2, slope=0.1)
-    os.environ["IRR_CORR_NO_PRETAB"] = "1"
-    try:
-        assert torch.equal(ops.warp_correlation(f1, f2, smooth, 436, 1024, 0.05, shift=B // 2, slope=0.1), fused_pre)
-    finally:
-        del os.environ["IRR_CORR_NO_PRETAB"]
+    # ... and so do the two experimental variants kept for A/B runs (both measured slower): the tap table
+    # from a pre-pass (IRR_CORR_PRETAB=1) and 7-row tiles with 8 compute warps (IRR_CORR_TH7=1)
+    from irr_b200 import ops as _ops
+    fused_ref = ops.warp_correlation(f1, f2, smooth, 436, 1024, 0.05, shift=B // 2, slope=0.1)
+    for var in ({"IRR_CORR_PRETAB": "1"}, {"IRR_CORR_TH7": "1"}, {"IRR_CORR_PRETAB": "1", "IRR_CORR_TH7": "1"}):
+        os.environ.update(var)
+        _ops._corr_ws_bytes.clear()   # the workspace size depends on the variant
+        try:
+            assert torch.equal(ops.warp_correlation(f1, f2, smooth, 436, 1024, 0.05, shift=B // 2, slope=0.1), fused_ref), var
+        finally:
+            for k in var:
+                del os.environ[k]
+            _ops._corr_ws_bytes.clear()
     wild = torch.randn(B, 2, H, W, generator=g).to(cuda) * 3.0      # divergent flow: tiles fall back to global gathers
     fw = ops.warp_correlation(f1, f2, wild, 436, 1024, 0.05, shift=B // 2)
     assert (fw - ops.correlation(f1, ops.warp(f2, wild, 436, 1024, 0.05, shift=B // 2))).abs().max().item() <= 1e-6
