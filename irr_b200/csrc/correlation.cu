@@ -33,11 +33,16 @@
 #ifndef IRR_CORR_TH
 #define IRR_CORR_TH 8
 #endif
-#if IRR_CORR_TH == 8
+#ifndef IRR_CORR_FP_H
+#define IRR_CORR_FP_H 24   // rows of the fused kernel's source-footprint window
+#endif
+#ifndef IRR_CORR_NFS
+#define IRR_CORR_NFS 2     // footprint ring depth
+#endif
+#ifndef IRR_CORR_NS
 #define IRR_CORR_NS corr8
 #else
-#define IRR_CORR_NS corr7
-#define IRR_CORR_VARIANT_ONLY 1
+#define IRR_CORR_VARIANT_ONLY 1   // secondary translation unit: only launch_corr_fused_variant is used
 #endif
 
 namespace irr {
@@ -59,7 +64,7 @@ constexpr int F2_ELEMS = CC * F2_H * F2_P;  // 5632
 constexpr int STAGE_ELEMS = F1_ELEMS + F2_ELEMS;
 constexpr int NHALO = F2_H * F2_WV;         // 640
 constexpr int NF1 = TH * TW;                // 256
-constexpr int FP_H = 24, FP_W = 48;            // fused variant: source footprint window per channel (texels)
+constexpr int FP_H = IRR_CORR_FP_H, FP_W = 48; // fused variant: source footprint window per channel (texels)
 constexpr int FP_ELEMS = CC * FP_H * FP_W;     // 9216 floats per ring slot
 constexpr int CORR_SMEM_PLAIN = CORR_STAGES * STAGE_ELEMS * 4 + 64;
 constexpr int CORR_SMEM_FUSED = CORR_SMEM_PLAIN + CORR_STAGES * FP_ELEMS * 4;
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
 // warps — at the one point where their 72 accumulators are dead and they would otherwise wait for the samplers — into
 // a double-buffered shared-memory table; the samplers and the copy issuer only read it (ncu: with the set-up on the
 // sampler warps it was 48 % of their time and the compute warps waited 43 % of theirs).
-constexpr int T_NS_PLAIN = 6, T_NS_FUSED = 3, T_NFS = 2;
+constexpr int T_NS_PLAIN = 6, T_NS_FUSED = 3, T_NFS = IRR_CORR_NFS;
 constexpr int T_PLAIN_THREADS = NCOMP + 32;   // plain: 9 compute warps + the issuer's warp (no register cap at 128)
 constexpr int T_NSAMP = 192;                  // sampler threads (warps 9-11, 13-15)
 // Warp w issues on scheduler w % 4: compute warps 0-8 load the schedulers 3:2:2:2, so the six sampler warps go to
@@ -1197,12 +1202,17 @@ int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, 
 
 #ifndef IRR_CORR_VARIANT_ONLY
 namespace irr {
-namespace corr7 {
+namespace corr7 {   // correlation7.cu: 7-row tiles
 int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                               const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
                               int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t corr_workspace_bytes(int B, int C, int H, int W, int fused);
 }  // namespace corr7
+namespace corrb {   // correlation_b.cu: 8-row tiles, 20-row footprint window, 3 footprint slots
+int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
+                              const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
+                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace corrb
 }  // namespace irr
 
 using namespace irr;
@@ -1254,6 +1264,12 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
   }
   IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
+  {
+    const char* e = getenv("IRR_CORR_VARB");   // experimental: deeper footprint ring (correlation_b.cu)
+    if (e && e[0] == '1')
+      return corrb::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
+                                              f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));
+  }
   if (!corr_force_th8())   // experimental: 7-row tiles, 8 compute warps, two per scheduler (correlation7.cu)
     return corr7::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
                                             f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));

@@ -61,9 +61,12 @@ class ConvBlock(nn.Sequential):
         math = self._math()
         w, b = self[0].weight, self[0].bias
         if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
-            if out is not None or addend is not None or alpha != 1.0 or x_fmt or y_fmt or add_fmt:
+            fused = out is not None or addend is not None or alpha != 1.0 or x_fmt or y_fmt or add_fmt
+            if not fused:
+                return _ConvFunction.apply(x, w, b, self, math)
+            if x.requires_grad:   # a live autograd graph reaches an inference-only form: refuse rather than cut it silently
                 raise RuntimeError("irr_b200.conv: the fused out= / addend= / alpha / format forms are inference-only")
-            return _ConvFunction.apply(x, w, b, self, math)
+            # parameters merely left at requires_grad=True outside torch.no_grad(): the inference kernel, as always
         return ops.conv2d(x, self.packed(math), b, self.cout, self.ks, self.stride, self.dil,
                           slope=self.slope, out=out, addend=addend, alpha=alpha, math=math, x_fmt=x_fmt, y_fmt=y_fmt,
                           add_fmt=add_fmt)
