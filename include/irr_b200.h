@@ -149,22 +149,6 @@ int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, co
                         long long addend2_bs, float* y2, long long y2_bs, float leaky_slope2, float alpha2, int math,
                         void* workspace, size_t workspace_bytes, irr_stream_t stream);
 
-/* Thin 3x3 layers chained at full resolution (OccUpsampleNetwork, models/irr_modules.py:46-56: 32 -> 32 five times) can
- * hand their activations on in the form the tensor-core path consumes, so the consumer skips its fp32 -> f16 {hi, lo}
- * conversion pass (37 % of its producers' time, profiles/r02_roll_counters_rowstage.txt):
- *   IRR_FMT_SPLIT16: a B x C x H x W fp32-sized tensor (C even) whose planes (2k, 2k+1) hold, per pixel, the u32 words
- *   { f16 hi(ch 2k) | f16 hi(ch 2k+1) << 16 } and { f16 lo(ch 2k) | f16 lo(ch 2k+1) << 16 }, hi = f16(v), lo = f16(v - hi).
- * hi + lo carries 22 significant bits; as a conv INPUT it is bit-identical to converting the fp32 tensor (that is the
- * conversion), as a residual addend it differs from the fp32 value by <= 2^-22 relative.  Only the row-rolling kernel
- * understands it (3x3, stride 1, dilation 1, Cin <= 32 even, Cout <= 32, W >= 96, W % 4 == 0, 16-byte aligned x); any
- * other request returns IRR_E_UNSUPPORTED.  y_format / addend_format = SPLIT16 need Cout % 16 == 0. */
-#define IRR_FMT_F32 0
-#define IRR_FMT_SPLIT16 1
-int irr_conv2d_fwd_fmt(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
-                       long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
-                       int stride, int dilation, float leaky_slope, float alpha, int math, int x_format, int y_format,
-                       int addend_format, irr_stream_t stream);
-
 /* The general form of the two above (IRR_MATH_TC_3XF16 only): the output channels are cut into up to IRR_CONV_MAX_SEGS
  * consecutive segments, segment i = channels [n_begin_i, n_begin_{i+1}) (n_begin_0 = 0, every n_begin a multiple of 16),
  * each with its own destination slice and epilogue

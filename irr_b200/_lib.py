@@ -48,8 +48,6 @@ PROTOTYPES = {
     "irr_conv2d_pack_weights": [c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp],
     "irr_conv2d_fwd": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                        c_f, c_i, c_fp],
-    "irr_conv2d_fwd_fmt": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_i,
-                           c_i, c_i, c_i, c_fp],
     "irr_conv2d_workspace_bytes": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i],
     "irr_conv2d_fwd_ws": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                           c_f, c_i, c_fp, C.c_size_t, c_fp],

@@ -23,8 +23,7 @@ struct HSeg {  // must match conv_tc16.cu
   float* y; long long y_bs;
 };
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const HSeg* segs, int nseg, int B, int Cin,
-             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st, int x_fmt = 0,
-             int y_fmt = 0, int a_fmt = 0);
+             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil);
 }  // namespace irr
 
@@ -110,22 +109,6 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
                     as_stream(stream));
   }
   return fail_arg(fn, "unknown math mode");
-}
-
-int irr_conv2d_fwd_fmt(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
-                       long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
-                       int stride, int dilation, float leaky_slope, float alpha, int math, int x_format, int y_format,
-                       int addend_format, irr_stream_t stream) {
-  const char* fn = "irr_conv2d_fwd_fmt";
-  IRR_REQUIRE(x && w_packed && bias && y, fn, "null pointer");
-  IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
-  IRR_REQUIRE(ksize == 3 && stride == 1 && dilation == 1, fn, "split-format tensors: 3x3, stride 1, dilation 1 only");
-  IRR_REQUIRE(math == IRR_MATH_TC_3XF16, fn, "split-format tensors are implemented by the IRR_MATH_TC_3XF16 path only");
-  IRR_REQUIRE((x_format | y_format | addend_format) >= 0 && x_format <= 1 && y_format <= 1 && addend_format <= 1, fn, "unknown format");
-  IRR_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, fn, "w_packed must be 16-byte aligned");
-  HSeg sg = {0, 0, leaky_slope, alpha, addend, addend_bs, y, y_bs};
-  return h16_conv(x, x_bs, w_packed, bias, &sg, 1, B, Cin, H, W, Cout, ksize, stride, dilation, nullptr, 0, as_stream(stream),
-                  x_format, y_format, addend_format);
 }
 
 int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,

@@ -692,8 +692,6 @@ struct RArgs {
   int L, segs, xtiles, items;
   float slope, alpha;
   int unordered;   // debug A/B only (IRR_ROLL_UNORDERED=1): skip the tap-row order tokens (results then vary in the last ulp)
-  // IRR_FMT_SPLIT16 tensors (include/irr_b200.h): x arrives / y leaves / the addend is read as f16 {hi | lo} plane pairs
-  int x_split, y_split, a_split;
 };
 
 template <int NG, bool CTR>
@@ -775,7 +773,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         // 16 pairs x 136 positions = 17 (pair, position) units per thread, consecutive threads on consecutive positions
         // (all loads first, then the math, then all stores: the compiler cannot prove the in-place stores do not
         // alias later loads and would otherwise serialise the 17 load -> split -> store chains)
-        if (!p.x_split) {   // (a SPLIT16 input arrives in exactly the form this pass produces: nothing to do)
         float cv0[17], cv1[17];
         int coff[17];
 #pragma unroll
@@ -802,7 +799,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         }
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
         H_ACC(1);
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + pt + 3;  // column of tap kx = 0 (4 - pad)
         // One A stage per input ROW: its three kx-shifted views go to three 32-column blocks of row stage cx % R_SR and
@@ -975,16 +971,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                 if (j < ctail) add[g * 16 + j] = __ldg(ap + (size_t)(g * 16 + j) * HW);
             }
           }
-          if (p.a_split) {   // SPLIT16 residual: planes (2k, 2k+1) = {hi(2k)|hi(2k+1)}, {lo(2k)|lo(2k+1)} -> hi + lo
-#pragma unroll
-            for (int k = 0; k < NG * 8; ++k) {
-              float h0, h1, l0, l1;
-              h_unpack(__float_as_uint(add[2 * k]), h0, h1);
-              h_unpack(__float_as_uint(add[2 * k + 1]), l0, l1);
-              add[2 * k] = h0 + l0;
-              add[2 * k + 1] = h1 + l1;
-            }
-          }
         }
         H_T0();
         mbar_wait(acc_full(slot), (uint32_t)((og >> 2) & 1));
@@ -1015,17 +1001,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
           for (int j = 0; j < 16; ++j) {
             const float a = fmaf(__uint_as_float(r[g * 16 + j]), inv_scale, bs[j]);
             val[j] = fmaf(leaky(a, slope), alpha, add[g * 16 + j]);
-          }
-          if (p.y_split) {   // SPLIT16 output: the next rolling layer's producers (and its residual) take it as is
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t hi = h_pack(val[2 * k], val[2 * k + 1]);
-              float f0, f1;
-              h_unpack(hi, f0, f1);
-              const uint32_t lo = h_pack(val[2 * k] - f0, val[2 * k + 1] - f1);
-              val[2 * k] = __uint_as_float(hi);
-              val[2 * k + 1] = __uint_as_float(lo);
-            }
           }
           if (m_ok) {
             if (g < cfull) {
@@ -1229,8 +1204,7 @@ size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int s
 }
 
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const HSeg* segs, int nseg, int B, int Cin,
-             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st, int x_fmt,
-             int y_fmt, int a_fmt) {
+             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st) {
   HGeom g = h_geom(Cout, Cin, ks);
   HArgs a;
   memset(&a, 0, sizeof(a));
@@ -1261,17 +1235,13 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   // ---- rolling kernel: single-chunk thin layers on wide images
-  const bool any_fmt = x_fmt != 0 || y_fmt != 0 || a_fmt != 0;
-  const bool fmt_ok = (!x_fmt || (Cin & 1) == 0) && (!y_fmt || (Cout & 15) == 0) && (!a_fmt || ((Cout & 15) == 0 && addend != nullptr));
-  if (tma_ok && (!no_roll() || any_fmt) && fmt_ok && single && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 &&
-      W >= 96) {
+  if (tma_ok && !no_roll() && single && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
     RArgs r;
     memset(&r, 0, sizeof(r));
     r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
     r.B = B; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.n_tile = g.n_tile;
     r.slope = slope; r.alpha = alpha;
     { const char* e = getenv("IRR_ROLL_UNORDERED"); r.unordered = (e && e[0] == '1') ? 1 : 0; }
-    r.x_split = x_fmt; r.y_split = y_fmt; r.a_split = a_fmt;
     r.xtiles = (W + 127) / 128;
     int L = 32;
     while (L > 4 && (long long)B * r.xtiles * ((H + L - 1) / L) < 3LL * sm_count()) L >>= 1;
@@ -1294,11 +1264,6 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
       else rc = dbg ? launch_roll<2, true>(map, r, rsmem, grid, st) : launch_roll<2, false>(map, r, rsmem, grid, st);
       return rc;
     }
-  }
-  if (any_fmt) {
-    set_error("irr_conv2d_fwd_fmt: IRR_FMT_SPLIT16 tensors are only understood by the row-rolling kernel (3x3, stride 1, "
-              "dilation 1, Cin <= 32, Cout <= 32, W >= 96, W %% 4 == 0, 16-byte aligned x)");
-    return IRR_E_UNSUPPORTED;
   }
   bool staged = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;

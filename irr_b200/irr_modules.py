@@ -31,17 +31,13 @@ class OccUpsampleNetwork(nn.Module):
 
     def forward_into(self, x_in):
         """x_in: (B, ch_in, H, W) buffer whose channel 0 already holds the x2-upsampled occlusion map."""
-        # At full resolution the 32-channel intermediates of the chain go from layer to layer as f16 {hi | lo} plane
-        # pairs (ops.FMT_SPLIT16: the consumer's conversion pass disappears; as conv inputs they are bit-identical to
-        # fp32 storage, as residuals they differ by <= 2^-22 relative).  Only x_in and the result are fp32.
-        S = ops.FMT_SPLIT16 if ops.split16_chain_ok(x_in, self.init_conv._math()) else ops.FMT_F32
-        x_init = self.init_conv(x_in, y_fmt=S)
+        x_init = self.init_conv(x_in)
         r = x_init
         for _ in range(3):  # shared weights, irr_modules.py:51-53
-            t = self.res_convs[0](r, x_fmt=S, y_fmt=S)
-            r = self.res_convs[1](t, addend=r, alpha=self.mul_const, x_fmt=S, y_fmt=S, add_fmt=S)
-        x_init2 = self.res_end_conv(r, addend=x_init, x_fmt=S, y_fmt=S, add_fmt=S)
-        return self.out_convs(x_init2, addend=x_in[:, 0:1], x_fmt=S)
+            t = self.res_convs[0](r)
+            r = self.res_convs[1](t, addend=r, alpha=self.mul_const)
+        x_init2 = self.res_end_conv(r, addend=x_init)
+        return self.out_convs(x_init2, addend=x_in[:, 0:1])
 
     def forward(self, occ, x):
         B, C, H, W = x.shape

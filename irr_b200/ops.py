@@ -231,23 +231,8 @@ def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
 _ws_bytes = {}
 
 
-FMT_F32 = 0
-FMT_SPLIT16 = 1   # f16 {hi | lo} plane pairs (include/irr_b200.h): what chained rolling-kernel layers hand to each other
-
-
-def split16_chain_ok(x, math: int) -> bool:
-    """True when 3x3 / stride 1 layers with <= 32 even channels over tensors shaped like ``x`` run on the row-rolling
-    kernel, i.e. may exchange IRR_FMT_SPLIT16 activations (the conditions of irr_conv2d_fwd_fmt)."""
-    import os
-    B, C, H, W = x.shape
-    return (math == MATH_TC_3XF16 and W >= 96 and W % 4 == 0 and x.data_ptr() % 16 == 0
-            and os.environ.get("IRR_CONV_NO_ROLL") != "1" and os.environ.get("IRR_CONV_GATHER") != "1"
-            and os.environ.get("IRR_NO_SPLIT16") != "1")
-
-
 def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, slope: float = 0.1, out=None,
-           addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT, x_fmt: int = FMT_F32, y_fmt: int = FMT_F32,
-           add_fmt: int = FMT_F32):
+           addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT):
     B, Cin, H, W = x.shape
     Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
     if out is None:
@@ -258,11 +243,6 @@ def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, s
     if addend is not None:
         assert addend.shape == out.shape
     lib = _lib.load()
-    if x_fmt or y_fmt or add_fmt:
-        _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_fmt, px, sx,
-                _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil,
-                slope, alpha, math, x_fmt, y_fmt, add_fmt, _stream())
-        return out
     # split-K scratch for layers with far fewer tiles than SMs (coarse pyramid levels); 0 bytes = never split
     key = (B, Cin, H, W, Cout, ks, stride, dil, math)
     nws = _ws_bytes.get(key)

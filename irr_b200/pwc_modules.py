@@ -57,19 +57,18 @@ class ConvBlock(nn.Sequential):
             self._packed[math] = hit
         return hit[1]
 
-    def forward(self, x, out=None, addend=None, alpha=1.0, x_fmt=0, y_fmt=0, add_fmt=0):
+    def forward(self, x, out=None, addend=None, alpha=1.0):
         math = self._math()
         w, b = self[0].weight, self[0].bias
         if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
-            fused = out is not None or addend is not None or alpha != 1.0 or x_fmt or y_fmt or add_fmt
+            fused = out is not None or addend is not None or alpha != 1.0
             if not fused:
                 return _ConvFunction.apply(x, w, b, self, math)
             if x.requires_grad:   # a live autograd graph reaches an inference-only form: refuse rather than cut it silently
-                raise RuntimeError("irr_b200.conv: the fused out= / addend= / alpha / format forms are inference-only")
+                raise RuntimeError("irr_b200.conv: the fused out= / addend= / alpha forms are inference-only")
             # parameters merely left at requires_grad=True outside torch.no_grad(): the inference kernel, as always
         return ops.conv2d(x, self.packed(math), b, self.cout, self.ks, self.stride, self.dil,
-                          slope=self.slope, out=out, addend=addend, alpha=alpha, math=math, x_fmt=x_fmt, y_fmt=y_fmt,
-                          add_fmt=add_fmt)
+                          slope=self.slope, out=out, addend=addend, alpha=alpha, math=math)
 
 
 class _ConvFunction(torch.autograd.Function):

@@ -506,39 +506,6 @@ def test_conv2d_3xf16_rolling_slices_addend(cuda):
     assert (out[:, :7] == 0).all() and (out[:, 39:] == 0).all()
 
 
-def test_conv2d_3xf16_split16_chain(cuda):
-    """IRR_FMT_SPLIT16 hand-off between rolling-kernel layers (irr_conv2d_fwd_fmt): a residual pair
-    r' = r + 0.1 * conv_b(lrelu(conv_a(r))) run (1) with fp32 intermediates and (2) with f16 {hi | lo} plane pairs for t, r
-    and r' — same results to 2^-22 relative, both against an fp64 reference; formats the other kernels cannot read are
-    refused."""
-    from irr_b200 import ops
-    import torch.nn.functional as F
-    B, H, W = 2, 37, 200
-    x11 = torch.from_numpy(rs(91, (B, 11, H, W)))
-    w0 = torch.from_numpy(rs(92, (32, 11, 3, 3))) * 0.1
-    wa = torch.from_numpy(rs(93, (32, 32, 3, 3))) * 0.06
-    wb = torch.from_numpy(rs(94, (32, 32, 3, 3))) * 0.06
-    b0, ba, bb = (torch.from_numpy(rs(95 + i, (32,))) * 0.1 for i in range(3))
-    r64 = F.leaky_relu(F.conv2d(x11.double(), w0.double(), b0.double(), padding=1), 0.1)
-    t64 = F.leaky_relu(F.conv2d(r64, wa.double(), ba.double(), padding=1), 0.1)
-    ref = r64 + 0.1 * F.conv2d(t64, wb.double(), bb.double(), padding=1)
-    M = ops.MATH_TC_3XF16
-    p0, pa, pb = (ops.pack_weights(w.to(cuda), M) for w in (w0, wa, wb))
-    xg = x11.to(cuda)
-    assert ops.split16_chain_ok(xg, M)
-    outs = {}
-    for S in (ops.FMT_F32, ops.FMT_SPLIT16):
-        r = ops.conv2d(xg, p0, b0.to(cuda), 32, 3, slope=0.1, math=M, y_fmt=S)
-        t = ops.conv2d(r, pa, ba.to(cuda), 32, 3, slope=0.1, math=M, x_fmt=S, y_fmt=S)
-        outs[S] = ops.conv2d(t, pb, bb.to(cuda), 32, 3, slope=1.0, math=M, addend=r, alpha=0.1, x_fmt=S, add_fmt=S)  # fp32 out
-    tol = 5e-5 * max(2.0, ref.abs().max().item())
-    assert (outs[0].cpu().double() - ref).abs().max().item() <= tol
-    assert (outs[1].cpu().double() - ref).abs().max().item() <= tol
-    assert (outs[0] - outs[1]).abs().max().item() <= 4e-6 * max(1.0, ref.abs().max().item())
-    with pytest.raises(RuntimeError):   # a 1x1 layer is not a rolling-kernel layer
-        ops.conv2d(xg, ops.pack_weights(torch.randn(32, 11, 1, 1, device=cuda), M), b0.to(cuda), 32, 1, math=M, y_fmt=ops.FMT_SPLIT16)
-
-
 @pytest.mark.parametrize("shape", [(2, 531, 20, 64, 2), (1, 530, 7, 16, 1), (2, 115, 33, 39, 2)])
 def test_conv2d_3xf16_dual_output(cuda, shape):
     """Fused conv5 + conv_last tail (irr_conv2d_fwd_dual) against two separate fp64 convs; includes a split-K shape and a
