@@ -1208,11 +1208,6 @@ int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, 
                               int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t corr_workspace_bytes(int B, int C, int H, int W, int fused);
 }  // namespace corr7
-namespace corrb {   // correlation_b.cu: 8-row tiles, 20-row footprint window, 3 footprint slots
-int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
-                              const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
-                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
-}  // namespace corrb
 }  // namespace irr
 
 using namespace irr;
@@ -1264,12 +1259,6 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
   }
   IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
-  {
-    const char* e = getenv("IRR_CORR_VARB");   // experimental: deeper footprint ring (correlation_b.cu)
-    if (e && e[0] == '1')
-      return corrb::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
-                                              f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));
-  }
   if (!corr_force_th8())   // experimental: 7-row tiles, 8 compute warps, two per scheduler (correlation7.cu)
     return corr7::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
                                             f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));

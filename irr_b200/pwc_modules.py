@@ -60,13 +60,13 @@ class ConvBlock(nn.Sequential):
     def forward(self, x, out=None, addend=None, alpha=1.0):
         math = self._math()
         w, b = self[0].weight, self[0].bias
-        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
-            fused = out is not None or addend is not None or alpha != 1.0
-            if not fused:
-                return _ConvFunction.apply(x, w, b, self, math)
-            if x.requires_grad:   # a live autograd graph reaches an inference-only form: refuse rather than cut it silently
+        # Autograd: a gradient is wanted when the input carries one, or when the block is in train
+        # mode with trainable parameters.  An .eval() model called outside torch.no_grad() — parameters still at
+        # requires_grad=True — runs the inference kernels, as the stage-level entry points always have.
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and (w.requires_grad or b.requires_grad))):
+            if out is not None or addend is not None or alpha != 1.0:
                 raise RuntimeError("irr_b200.conv: the fused out= / addend= / alpha forms are inference-only")
-            # parameters merely left at requires_grad=True outside torch.no_grad(): the inference kernel, as always
+            return _ConvFunction.apply(x, w, b, self, math)
         return ops.conv2d(x, self.packed(math), b, self.cout, self.ks, self.stride, self.dil,
                           slope=self.slope, out=out, addend=addend, alpha=alpha, math=math)
 
