@@ -23,6 +23,12 @@
  *     AT_ERROR -> RuntimeError by correlation_cuda.cc:78-80; the Python host in irr_b200/_lib.py raises
  *     RuntimeError on any non-zero return to keep that behaviour.)
  *   - re-entrant per stream; no global mutable state except the error string and one-time function attributes.
+ *   - ROW PITCH (ABI 2).  The spatial entry points take `*_pitch` arguments: the distance in elements between two rows
+ *     of a plane; channel stride = H * pitch; 0 means "dense" (= W).  A pitch that is a multiple of 4 makes every row
+ *     16-byte aligned whatever the width, which is what TMA needs: the host side stores KITTI's 621 / 311 / 78 / 39-wide
+ *     levels with pitch 624 / 312 / 80 / 40 (the reference handles odd sizes natively, models/irr_modules.py:21-27), the
+ *     tensor maps zero-fill columns >= W, and nobody reads or relies on the pad columns.  The flat kernels
+ *     (irr_scale_channels_fwd, irr_round_bf16_fwd, irr_channel_l2norm_fwd) take HW = H * pitch for such tensors.
  */
 #ifndef IRR_B200_H_
 #define IRR_B200_H_
@@ -35,7 +41,7 @@ extern "C" {
 
 typedef struct CUstream_st* irr_stream_t;
 
-#define IRR_ABI_VERSION 1
+#define IRR_ABI_VERSION 2   /* 2: row pitches (below), workspaces for the correlation, output segments for the conv */
 
 #define IRR_E_ARG (-1)       /* null pointer / non-positive size / unsupported parameter */
 #define IRR_E_ALIGN (-2)     /* pointer alignment requirement violated */
@@ -92,7 +98,7 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
                                 long long flow_bs, const float* lin_x, const float* lin_y, float* out, long long out_bs,
                                 int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
                                 int f2_batch_shift, float leaky_slope, int grid_flags, void* workspace,
-                                size_t workspace_bytes, irr_stream_t stream);
+                                size_t workspace_bytes, int pitch, irr_stream_t stream);
 
 /* A2 standalone — out[b] = mask*warp(x[(b+x_batch_shift) mod B], flow[b]);  if minuend != NULL:
  * out = minuend - mask*warp(...)   (IRR_PWC.py:132-133,144-145 feed `a - warp(b)` to the refinement nets).
@@ -100,7 +106,7 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
 int irr_warp_fwd(const float* x, long long x_bs, const float* flow, long long flow_bs, const float* lin_x,
                  const float* lin_y, const float* minuend, long long minuend_bs, float* out, long long out_bs,
                  float* mask_out, int B, int C, int H, int W, int H_im, int W_im, float div_flow, int x_batch_shift,
-                 int grid_flags, irr_stream_t stream);
+                 int grid_flags, int pitch, irr_stream_t stream);
 
 /* Generic Correlation (kernel_size odd >= 1, stride1, stride2, pad_size) for API completeness of
  * correlation_package/correlation.py:47-61; output shape per correlation_cuda.cc:23-32.  corr_type_multiply is
@@ -123,7 +129,8 @@ int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int C
                             irr_stream_t stream);
 int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
                    long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
-                   int stride, int dilation, float leaky_slope, float alpha, int math, irr_stream_t stream);
+                   int stride, int dilation, float leaky_slope, float alpha, int math, int x_pitch, int y_pitch,
+                   irr_stream_t stream);
 
 /* Same, with an optional scratch buffer that lets the tensor-core path split the K loop of a layer over several CTAs
  * when the layer has far fewer output tiles than the GPU has SMs (the 7x16 ... 14x32 pyramid levels): partial sums go
@@ -135,7 +142,7 @@ size_t irr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks
 int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
                       long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
                       int stride, int dilation, float leaky_slope, float alpha, int math, void* workspace,
-                      size_t workspace_bytes, irr_stream_t stream);
+                      size_t workspace_bytes, int x_pitch, int y_pitch, irr_stream_t stream);
 
 /* Two layers that read the same input in one pass (IRR_MATH_TC_3XF16 only): output channels [0, n_split) get the
  * first epilogue and go to y, channels [n_split, Cout) get (addend2, alpha2, leaky_slope2) and go to y2 (a
@@ -147,7 +154,7 @@ int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, co
                         long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
                         int stride, int dilation, float leaky_slope, float alpha, int n_split, const float* addend2,
                         long long addend2_bs, float* y2, long long y2_bs, float leaky_slope2, float alpha2, int math,
-                        void* workspace, size_t workspace_bytes, irr_stream_t stream);
+                        void* workspace, size_t workspace_bytes, int x_pitch, int y_pitch, irr_stream_t stream);
 
 /* The general form of the two above (IRR_MATH_TC_3XF16 only): the output channels are cut into up to IRR_CONV_MAX_SEGS
  * consecutive segments, segment i = channels [n_begin_i, n_begin_{i+1}) (n_begin_0 = 0, every n_begin a multiple of 16),
@@ -171,13 +178,14 @@ typedef struct irr_conv_seg {
 } irr_conv_seg;
 int irr_conv2d_fwd_multi(const float* x, long long x_bs, const void* w_packed, const float* bias, int B, int Cin, int H,
                          int W, int Cout, int ksize, int stride, int dilation, const irr_conv_seg* segs, int n_segs, int math,
-                         void* workspace, size_t workspace_bytes, irr_stream_t stream);
+                         void* workspace, size_t workspace_bytes, int x_pitch, int y_pitch, irr_stream_t stream);
 
 /* A8 — upsample2d_as (models/pwc_modules.py:65-67): bilinear, align_corners=True, any in/out size, fused with an
  * optional per-channel-parity scale (even channels * scale_even, odd * scale_odd): rescale_flow of
  * pwc_modules.py:70-82 applied to the resized flow, or the final *(1/div_flow) of IRR_PWC.py:176. */
 int irr_resize_bilinear_ac_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
-                               int OH, int OW, float scale_even, float scale_odd, irr_stream_t stream);
+                               int OH, int OW, float scale_even, float scale_odd, int x_pitch, int y_pitch,
+                               irr_stream_t stream);
 
 /* A8 — rescale_flow value semantics / channel-slice copy: y[b,c] = x[b,c] * (c even ? scale_even : scale_odd). */
 int irr_scale_channels_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
@@ -191,12 +199,12 @@ int irr_round_bf16_fwd(const float* x, long long x_bs, float* y, long long y_bs,
 /* A10 — upsample_factor2 (models/irr_modules.py:21-27): nearest x2, then (only if (OH,OW) != (2H,2W)) bilinear
  * align_corners=False resize to OH x OW. */
 int irr_upsample_nearest2x_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
-                               int OH, int OW, irr_stream_t stream);
+                               int OH, int OW, int x_pitch, int y_pitch, irr_stream_t stream);
 
 /* A9 head — RefineFlow input preparation (models/irr_modules.py:59-60,85-88):
  *   y[b,c] = x[b,c] - mean_w(mean_h(x[b,c]))  for C channels.  One CTA per (b,c). */
 int irr_sub_spatial_mean_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, int H, int W,
-                             irr_stream_t stream);
+                             int pitch, irr_stream_t stream);
 /*   y[b,0] = sqrt(sum_c x[b,c]^2)   (torch.norm(p=2, dim=1), irr_modules.py:86). */
 int irr_channel_l2norm_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
                            irr_stream_t stream);
@@ -204,7 +212,7 @@ int irr_channel_l2norm_fwd(const float* x, long long x_bs, float* y, long long y
 /* A9 tail — softmax(-logits^2) over the 9 taps, applied to the replicate-padded 3x3 neighbourhood of every
  * channel of src (models/irr_modules.py:89-104, 130-138).  logits: B x 9 x H x W, src/out: B x C x H x W. */
 int irr_refine_gather_fwd(const float* logits, long long logits_bs, const float* src, long long src_bs, float* out,
-                          long long out_bs, int B, int C, int H, int W, irr_stream_t stream);
+                          long long out_bs, int B, int C, int H, int W, int pitch, irr_stream_t stream);
 
 /* §8(f).4 — backward of the cost volume for the PWC parameters (pad 4, k 1, md 4, stride 1/1): replaces
  * correlation_cuda.backward -> correlation_backward_input1/_input2 (correlation_cuda.cc:86-163,

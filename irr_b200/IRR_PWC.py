@@ -108,6 +108,7 @@ class PWCNet(nn.Module):
         occ_up : (2B, 1, h, w)
         imgs   : (2B, 3, H, W)
         returns (flow, occ) for this level (flow in GLOBAL units), each on the 2B batch."""
+        feat, flow_up, occ_up, imgs = ops.pitched(feat), ops.pitched(flow_up), ops.pitched(occ_up), ops.pitched(imgs)
         B2, C, h, w = feat.shape
         B = B2 // 2
         dev = feat.device
@@ -116,9 +117,9 @@ class PWCNet(nn.Module):
         rec = (lambda k, v: record.__setitem__(k, v.clone())) if record is not None else (lambda k, v: None)
 
         # estimator input buffers: [448 dense outputs | corr 81 | x_1by1 32 | flow 2 or occ 1 | est 2 or 1]
-        buf_f = torch.empty((B2, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
+        buf_f = ops.empty(B2, 448 + nf + 2, h, w, dev)
         BO = B if self.eval_prune_dead else B2   # rows the occlusion branch runs on
-        buf_o = torch.empty((BO, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
+        buf_o = ops.empty(BO, 448 + no + 1, h, w, dev)
         corr = buf_f[:, 448:529]
         if l == 0:  # IRR_PWC.py:78-80,90-95 — no warp at the coarsest level
             ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
@@ -160,26 +161,31 @@ class PWCNet(nn.Module):
         """IRR_PWC.py:126-138.  ``flow_cont`` arrives in LOCAL units and is converted IN PLACE to global units first —
         exactly what the un-rebound rescale_flow call at :128-129 leaves behind, so RefineFlow (:132-133)
         sees global units; its output is then scaled to global once more (:137-138)."""
+        flow_cont_arg = flow_cont
+        flow_cont, x1by1, imgs = ops.pitched(flow_cont), ops.pitched(x1by1), ops.pitched(imgs)
         B2, _, h, w = flow_cont.shape
         B = B2 // 2
         df = self._div_flow
         su_g, sv_g = flow_scales(h, w, df, width_im, height_im, False)
         img_r = ops.resize_ac(imgs, h, w)  # :126-127
         ops.scale_channels(flow_cont, out=flow_cont, s_even=su_g, s_odd=sv_g)
-        rf_in = torch.empty((B2, 35, h, w), dtype=torch.float32, device=flow_cont.device)
+        rf_in = ops.empty(B2, 35, h, w, flow_cont.device)
         diff = ops.warp(img_r, flow_cont, height_im, width_im, df, minuend=img_r, shift=B)  # img_a - warp(img_b)
         ops.sub_spatial_mean(flow_cont, out=rf_in[:, 0:2])
         ops.channel_l2norm(diff, out=rf_in[:, 2:3])
         ops.scale_channels(x1by1, out=rf_in[:, 3:35])
         flow = self.refine_flow.gather(rf_in, flow_cont)
         ops.scale_channels(flow, out=flow, s_even=su_g, s_odd=sv_g)
+        if flow_cont is not flow_cont_arg:   # a dense argument was re-pitched: keep the in-place side effect visible (F6)
+            ops.scale_channels(flow_cont, out=flow_cont_arg)
         return flow
 
     def refine_occ_stage(self, occ_cont, x1by1, flow, height_im, width_im):
         """IRR_PWC.py:141-145: occ = RefineOcc(occ_cont, x_1by1, x_1by1 - warp(other x_1by1, flow))."""
+        occ_cont, x1by1, flow = ops.pitched(occ_cont), ops.pitched(x1by1), ops.pitched(flow)
         BO, _, h, w = occ_cont.shape
         B = x1by1.shape[0] // 2
-        ro_in = torch.empty((BO, 65, h, w), dtype=torch.float32, device=occ_cont.device)
+        ro_in = ops.empty(BO, 65, h, w, occ_cont.device)
         ops.scale_channels(occ_cont, out=ro_in[:, 0:1])
         ops.scale_channels(x1by1[:BO], out=ro_in[:, 1:33])
         if BO == 2 * B:
@@ -190,11 +196,12 @@ class PWCNet(nn.Module):
 
     def upsample_level(self, l, feat, flow, occ_prev, height_im, width_im, record=None):
         """IRR_PWC.py:150-174 for l in {5, 6}: occlusion up-sampling guided by warped features / flows."""
+        feat, flow, occ_prev = ops.pitched(feat), ops.pitched(flow), ops.pitched(occ_prev)
         B2, C, h, w = feat.shape
         B = B2 // 2
         df = self._div_flow
         if occ_prev.shape[0] == B:  # eval_prune_dead: forward rows only (IRR_PWC.py:155,157,172 for occ_f)
-            x_in = torch.empty((B, 11, h, w), dtype=torch.float32, device=feat.device)
+            x_in = ops.empty(B, 11, h, w, feat.device)
             ops.upsample_nearest2x(occ_prev, h, w, out=x_in[:, 0:1])
             if l != self.num_levels - 1:
                 self.conv_1x1_1(feat[:B], out=x_in[:, 1:4])
@@ -206,7 +213,7 @@ class PWCNet(nn.Module):
             ops.scale_channels(flow[:B], out=x_in[:, 7:9])
             ops.warp(flow[B:], flow[:B], height_im, width_im, df, out=x_in[:, 9:11])  # flow_b warped by flow_f
         else:
-            x_in = torch.empty((B2, 11, h, w), dtype=torch.float32, device=feat.device)
+            x_in = ops.empty(B2, 11, h, w, feat.device)
             ops.upsample_nearest2x(occ_prev, h, w, out=x_in[:, 0:1])
             if l != self.num_levels - 1:  # :160-164
                 self.conv_1x1_1(feat, out=x_in[:, 1:4])
@@ -230,7 +237,7 @@ class PWCNet(nn.Module):
         x2_raw = input_dict['input2']
         B, _, height_im, width_im = x1_raw.shape
         with torch.no_grad():
-            imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()  # (2B, 3, H, W)
+            imgs = ops.stack_pair(x1_raw, x2_raw)  # (2B, 3, H, W), rows pitched when W % 4 != 0
             pyramid = self.feature_pyramid_extractor(imgs)
             if self.feature_dtype == "bf16":
                 for f in pyramid:
@@ -245,8 +252,8 @@ class PWCNet(nn.Module):
                     record[l] = rec_l
                 if l <= self.output_level:
                     if l == 0:
-                        flow_up = torch.zeros((2 * B, 2, h, w), dtype=torch.float32, device=imgs.device)
-                        occ_up = torch.zeros((2 * B, 1, h, w), dtype=torch.float32, device=imgs.device)
+                        flow_up = ops.empty(2 * B, 2, h, w, imgs.device, zero=True)
+                        occ_up = ops.empty(2 * B, 1, h, w, imgs.device, zero=True)
                     else:
                         flow_up = ops.resize_ac(flow, h, w)
                         occ_up = ops.resize_ac(occ, h, w)
@@ -259,6 +266,6 @@ class PWCNet(nn.Module):
                         rec_l["feat"] = feat.clone(); rec_l["flow_up"] = flow.clone(); rec_l["occ_in"] = occ.clone()
                     occ = self.upsample_level(l, feat, flow, occ, height_im, width_im, rec_l)
             out_flow = ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / self._div_flow,
-                                     s_odd=1.0 / self._div_flow)  # :176
-            out_occ = ops.resize_ac(occ[:B], height_im, width_im)  # :177
+                                     s_odd=1.0 / self._div_flow, pitched=False)  # :176 (user-facing: dense rows)
+            out_occ = ops.resize_ac(occ[:B], height_im, width_im, pitched=False)  # :177
         return {'flow': out_flow, 'occ': out_occ}

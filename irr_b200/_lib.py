@@ -35,9 +35,9 @@ PROTOTYPES = {
                                  c_i, c_f, c_i, c_i, c_f, c_i, c_fp],
     "irr_correlation_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
     "irr_warp_correlation_fwd_ws": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i,
-                                    c_i, c_f, c_i, c_i, c_f, c_i, c_fp, C.c_size_t, c_fp],
+                                    c_i, c_f, c_i, c_i, c_f, c_i, c_fp, C.c_size_t, c_i, c_fp],
     "irr_warp_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_i, c_i, c_i,
-                     c_f, c_i, c_i, c_fp],
+                     c_f, c_i, c_i, c_i, c_fp],
     "irr_warp_bwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                      c_i, c_fp],
     "irr_correlation_generic_fwd": [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
@@ -47,23 +47,23 @@ PROTOTYPES = {
     "irr_conv2d_math_supported": [c_i, c_i, c_i, c_i, c_i, c_i],
     "irr_conv2d_pack_weights": [c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp],
     "irr_conv2d_fwd": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
-                       c_f, c_i, c_fp],
+                       c_f, c_i, c_i, c_i, c_fp],
     "irr_conv2d_workspace_bytes": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i],
     "irr_conv2d_fwd_ws": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
-                          c_f, c_i, c_fp, C.c_size_t, c_fp],
+                          c_f, c_i, c_fp, C.c_size_t, c_i, c_i, c_fp],
     "irr_conv2d_fwd_dual": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
-                            c_f, c_i, c_fp, c_ll, c_fp, c_ll, c_f, c_f, c_i, c_fp, C.c_size_t, c_fp],
+                            c_f, c_i, c_fp, c_ll, c_fp, c_ll, c_f, c_f, c_i, c_fp, C.c_size_t, c_i, c_i, c_fp],
     "irr_conv2d_fwd_multi": [c_fp, c_ll, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, C.POINTER(ConvSeg), c_i, c_i, c_fp,
-                             C.c_size_t, c_fp],
-    "irr_resize_bilinear_ac_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_fp],
+                             C.c_size_t, c_i, c_i, c_fp],
+    "irr_resize_bilinear_ac_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_i, c_i, c_fp],
     "irr_scale_channels_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_f, c_f, c_fp],
     "irr_round_bf16_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],
-    "irr_upsample_nearest2x_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
-    "irr_sub_spatial_mean_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
+    "irr_upsample_nearest2x_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp],
+    "irr_sub_spatial_mean_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_channel_l2norm_fwd": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_ll, c_fp],
     "irr_correlation_bwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_eval_metrics_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_fp],
-    "irr_refine_gather_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_fp],
+    "irr_refine_gather_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_fp],
 }
 _RESTYPES = {"irr_last_error": C.c_char_p, "irr_conv2d_packed_bytes": C.c_size_t,
              "irr_conv2d_workspace_bytes": C.c_size_t, "irr_correlation_workspace_bytes": C.c_size_t}
@@ -85,7 +85,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI drift
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, c_i)
-    if lib.irr_abi_version() != 1:
+    if lib.irr_abi_version() != 2:
         raise RuntimeError("irr_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -63,13 +63,14 @@ EncodeTiledFn encode_tiled() {
 }
 
 bool make_nchw_map(CUtensorMap* map, const float* base, long long bs, int B, int C, int H, int W, int bw, int bh,
-                   int bc) {
+                   int bc, int pitch) {
   EncodeTiledFn enc = encode_tiled();
-  if (!enc || (W % 4) != 0 || (bs % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  const int P = pitch > 0 ? pitch : W;   // row pitch in elements; the map's inner dimension stays W: columns >= W read 0
+  if (!enc || (P % 4) != 0 || P < W || (bs % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
   if (bw > 256 || bh > 256 || bc > 256 || ((bw * 4) % 16) != 0) return false;
   memset(map, 0, sizeof(*map));
   cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)bs * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)P * 4, (cuuint64_t)H * P * 4, (cuuint64_t)bs * 4};
   cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,

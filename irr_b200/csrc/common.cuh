@@ -48,7 +48,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_tiled();
 // fp32 NCHW channel-slice view (W, H, C, B; batch stride bs elements) -> tiled tensor map with the given box
 // (elements, innermost first).  Out-of-bounds box elements read as zero.  Needs W % 4 == 0, bs % 4 == 0, 16-byte base.
-bool make_nchw_map(CUtensorMap* map, const float* base, long long bs, int B, int C, int H, int W, int bw, int bh, int bc);
+bool make_nchw_map(CUtensorMap* map, const float* base, long long bs, int B, int C, int H, int W, int bw, int bh, int bc,
+                   int pitch = 0);
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
@@ -202,13 +203,14 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
 }
 
 // Gather one channel plane `p` (H x W) with taps t (weights of out-of-bounds taps are zero, so clamp addresses).
-__device__ __forceinline__ float gather_bilinear(const float* __restrict__ p, const Taps& t, int W, int H) {
+// `P` = row pitch of the plane in elements (>= W).
+__device__ __forceinline__ float gather_bilinear(const float* __restrict__ p, const Taps& t, int W, int H, int P) {
   int x0 = min(max(t.x0, 0), W - 1), x1 = min(max(t.x0 + 1, 0), W - 1);
   int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
-  float acc = __fmul_rn(__ldg(p + (size_t)y0 * W + x0), t.w00);  // same tap order as grid_sampler_2d_kernel
-  acc = fmaf(__ldg(p + (size_t)y0 * W + x1), t.w01, acc);
-  acc = fmaf(__ldg(p + (size_t)y1 * W + x0), t.w10, acc);
-  acc = fmaf(__ldg(p + (size_t)y1 * W + x1), t.w11, acc);
+  float acc = __fmul_rn(__ldg(p + (size_t)y0 * P + x0), t.w00);  // same tap order as grid_sampler_2d_kernel
+  acc = fmaf(__ldg(p + (size_t)y0 * P + x1), t.w01, acc);
+  acc = fmaf(__ldg(p + (size_t)y1 * P + x0), t.w10, acc);
+  acc = fmaf(__ldg(p + (size_t)y1 * P + x1), t.w11, acc);
   return acc;
 }
 

@@ -23,7 +23,8 @@ struct HSeg {  // must match conv_tc16.cu
   float* y; long long y_bs;
 };
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const HSeg* segs, int nseg, int B, int Cin,
-             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st);
+             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st, int pitch_in,
+             int pitch_out);
 size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil);
 }  // namespace irr
 
@@ -73,16 +74,20 @@ size_t irr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks
 
 int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
                    long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
-                   int stride, int dilation, float leaky_slope, float alpha, int math, irr_stream_t stream) {
+                   int stride, int dilation, float leaky_slope, float alpha, int math, int x_pitch, int y_pitch,
+                   irr_stream_t stream) {
   return irr_conv2d_fwd_ws(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride,
-                           dilation, leaky_slope, alpha, math, nullptr, 0, stream);
+                           dilation, leaky_slope, alpha, math, nullptr, 0, x_pitch, y_pitch, stream);
 }
 
 int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,
                       long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
                       int stride, int dilation, float leaky_slope, float alpha, int math, void* workspace,
-                      size_t workspace_bytes, irr_stream_t stream) {
+                      size_t workspace_bytes, int x_pitch, int y_pitch, irr_stream_t stream) {
   const char* fn = "irr_conv2d_fwd";
+  const bool pitched = (x_pitch > 0 && x_pitch != W) ||
+                       (y_pitch > 0 && y_pitch != (W + 2 * (((ksize - 1) * dilation) / 2) - dilation * (ksize - 1) - 1) / stride + 1);
+  IRR_REQUIRE(!pitched || math == IRR_MATH_TC_3XF16, fn, "row pitches are implemented by the IRR_MATH_TC_3XF16 path only");
   IRR_REQUIRE(x && w_packed && bias && y, fn, "null pointer");
   IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
   IRR_REQUIRE(ksize == 1 || ksize == 3, fn, "kernel_size must be 1 or 3");
@@ -106,7 +111,7 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
     }
     HSeg sg = {0, 0, leaky_slope, alpha, addend, addend_bs, y, y_bs};
     return h16_conv(x, x_bs, w_packed, bias, &sg, 1, B, Cin, H, W, Cout, ksize, stride, dilation, workspace, workspace_bytes,
-                    as_stream(stream));
+                    as_stream(stream), x_pitch, y_pitch);
   }
   return fail_arg(fn, "unknown math mode");
 }
@@ -115,7 +120,7 @@ int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, co
                         long long addend_bs, float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ksize,
                         int stride, int dilation, float leaky_slope, float alpha, int n_split, const float* addend2,
                         long long addend2_bs, float* y2, long long y2_bs, float leaky_slope2, float alpha2, int math,
-                        void* workspace, size_t workspace_bytes, irr_stream_t stream) {
+                        void* workspace, size_t workspace_bytes, int x_pitch, int y_pitch, irr_stream_t stream) {
   const char* fn = "irr_conv2d_fwd_dual";
   IRR_REQUIRE(x && w_packed && bias && y && y2, fn, "null pointer");
   IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
@@ -131,12 +136,12 @@ int irr_conv2d_fwd_dual(const float* x, long long x_bs, const void* w_packed, co
   HSeg sg[2] = {{0, 0, leaky_slope, alpha, addend, addend_bs, y, y_bs},
                 {n_split, 0, leaky_slope2, alpha2, addend2, addend2_bs, y2, y2_bs}};
   return h16_conv(x, x_bs, w_packed, bias, sg, 2, B, Cin, H, W, Cout, ksize, stride, dilation, workspace, workspace_bytes,
-                  as_stream(stream));
+                  as_stream(stream), x_pitch, y_pitch);
 }
 
 int irr_conv2d_fwd_multi(const float* x, long long x_bs, const void* w_packed, const float* bias, int B, int Cin, int H,
                          int W, int Cout, int ksize, int stride, int dilation, const irr_conv_seg* segs, int n_segs, int math,
-                         void* workspace, size_t workspace_bytes, irr_stream_t stream) {
+                         void* workspace, size_t workspace_bytes, int x_pitch, int y_pitch, irr_stream_t stream) {
   const char* fn = "irr_conv2d_fwd_multi";
   IRR_REQUIRE(x && w_packed && bias && segs, fn, "null pointer");
   IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
@@ -157,7 +162,7 @@ int irr_conv2d_fwd_multi(const float* x, long long x_bs, const void* w_packed, c
     sg[i].y_bs = segs[i].y_bs;
   }
   return h16_conv(x, x_bs, w_packed, bias, sg, n_segs, B, Cin, H, W, Cout, ksize, stride, dilation, workspace,
-                  workspace_bytes, as_stream(stream));
+                  workspace_bytes, as_stream(stream), x_pitch, y_pitch);
 }
 
 }  // extern "C"

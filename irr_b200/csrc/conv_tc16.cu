@@ -70,6 +70,7 @@ struct HArgs {
   const float* bias;
   HSegs seg;
   int B, Cin, H, W, Cout, Ho, Wo, stride, dil, pad;
+  int Pi, Po;                 // row pitch (elements) of the input / of the outputs and residuals (>= W / Wo)
   int n_tile, n_tiles, cchunks, nkb, sb, resident;
   unsigned b_smem_bytes, x_stage_bytes;
   int rw_log2, rh, R, PW, padl, split, ytiles, xtiles, m_items, items;
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
   const float inv_scale = __ldg(reinterpret_cast<const float*>(p.wp) + 1);
   const uint8_t* wimg = p.wp + H_HDR;
-  const int HWo = p.Ho * p.Wo;
+  const int HWo = p.Ho * p.Wo;           // output pixels per image (linear pixel decode of the gather variant)
+  const size_t CSo = (size_t)p.Ho * p.Po;  // output channel stride (pitched rows)
   const int RW = 1 << p.rw_log2;
   const int tiles_per_img = p.ytiles * p.xtiles;
 
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
     const int grp = warp >> 2, q = warp & 3;
     const int t = q * 32 + lane;                 // this thread's pixel index inside a half
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const size_t HW = (size_t)p.H * p.W;
+    const size_t HW = (size_t)p.H * p.Pi;   // input channel stride (pitched rows)
     // STAGED: word offsets of this thread's pixel (half 0 / half 1) inside an activation tile [32][R][PW]
     const int rin = t >> p.rw_log2, xin = t & (RW - 1);
     const int chp = p.R * p.PW;                  // plane pitch = positions per tile
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           for (int h = 0; h < 2; ++h) {
             const int iy = iy0[h] + ky * p.dil, ix = ix0[h] + kx * p.dil;
             const bool ok = m_ok[h] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-            const float* src = ok ? xb[h] + (size_t)c0 * HW + ((size_t)iy * p.W + ix) : h_zero_page;
+            const float* src = ok ? xb[h] + (size_t)c0 * HW + ((size_t)iy * p.Pi + ix) : h_zero_page;
             const unsigned cstride = ok ? (unsigned)HW : 0u;
             float v[H_CK];
             if (nch >= H_CK) {
@@ -568,14 +570,20 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           const int oy = y0 + h * p.rh + rin, ox = x0 + xin;
           m_ok = oy < p.Ho && ox < p.Wo;
           ob = ib;
-          opix = m_ok ? oy * p.Wo + ox : 0;
+          opix = m_ok ? oy * p.Po + ox : 0;
         } else {
           const long long mg = (long long)mt * 256 + h * 128 + t;
           m_ok = mg < p.M;
-          if (m_ok) { ob = (int)(mg / HWo); opix = (int)(mg - (long long)ob * HWo); }
+          if (m_ok) {
+            ob = (int)(mg / HWo);
+            const int rem = (int)(mg - (long long)ob * HWo);
+            const int oy = rem / p.Wo;
+            opix = oy * p.Po + (rem - oy * p.Wo);
+          }
         }
         const uint32_t acc_addr = lane_addr + (uint32_t)((buf * 2 + h) * acc_stride);
-        float* ywr = p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + opix;  // raw split-K partials
+        const int dpix = opix - (opix / p.Po) * (p.Po - p.Wo);   // dense pixel index (the split-K workspace is not pitched)
+        float* ywr = p.ws + (size_t)sp * p.ws_stride + (size_t)ob * p.Cout * HWo + dpix;  // raw split-K partials
         // output segments (fused tails of the dense estimators): every 16-channel group belongs to one segment with its
         // own destination, residual and activation — resolved once per segment, not per group; raw split-K partials keep
         // the single [Cout] layout
@@ -605,7 +613,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           float add[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            add[j] = (has_add && m_ok && j < nvalid) ? __ldg(ap + (size_t)(cb + j) * HWo) : 0.f;
+            add[j] = (has_add && m_ok && j < nvalid) ? __ldg(ap + (size_t)(cb + j) * CSo) : 0.f;
           uint32_t r[16];
           H_ACC(1);
           h_tmem_ld16(acc_addr + (uint32_t)c0, r);
@@ -627,11 +635,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_h16_kernel(const __grid_con
           if (m_ok) {
             if (nvalid == 16) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) yp[(size_t)(cb + j) * HWo] = val[j];
+              for (int j = 0; j < 16; ++j) yp[(size_t)(cb + j) * (raw ? (size_t)HWo : CSo)] = val[j];
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < nvalid) yp[(size_t)(cb + j) * HWo] = val[j];
+                if (j < nvalid) yp[(size_t)(cb + j) * (raw ? (size_t)HWo : CSo)] = val[j];
             }
           }
           H_ACC(3);
@@ -689,6 +697,7 @@ struct RArgs {
   const float* addend; long long a_bs;
   float* y; long long y_bs;
   int B, Cin, H, W, Cout, n_tile;
+  int Pi, Po;   // row pitch of the input / of the output and residual
   int L, segs, xtiles, items;
   float slope, alpha;
   int unordered;   // debug A/B only (IRR_ROLL_UNORDERED=1): skip the tap-row order tokens (results then vary in the last ulp)
@@ -740,7 +749,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
   h_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const float inv_scale = __ldg(reinterpret_cast<const float*>(p.wp) + 1);
-  const int HW = p.H * p.W;
+  const int HW = p.H * p.Po;   // channel stride of the output / residual (pitched rows)
   const int per_img = p.segs * p.xtiles;
 
   auto item_decode = [&](int item, int& b, int& ya, int& nr, int& x0) {
@@ -942,7 +951,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
       const bool m_ok = ox < p.W;
       for (int oi = 0; oi < nr; ++oi, ++og) {
         const int slot = og & 3;
-        const size_t opix = (size_t)(ya + oi) * p.W + (m_ok ? ox : 0);
+        const size_t opix = (size_t)(ya + oi) * p.Po + (m_ok ? ox : 0);
         float* yp = p.y + (size_t)b * p.y_bs + opix;
         // residual operand first: its loads are in flight while the row's last MMAs finish
         float add[NG * 16];
@@ -955,7 +964,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
           if (oi + 2 < nr) {
             const int pch = t >> 2, pxs = x0 + (t & 3) * 32;
             if (pch < p.Cout && pxs < p.W) {
-              const float* pa = p.addend + (size_t)b * p.a_bs + (size_t)pch * HW + (size_t)(ya + oi + 2) * p.W + pxs;
+              const float* pa = p.addend + (size_t)b * p.a_bs + (size_t)pch * HW + (size_t)(ya + oi + 2) * p.Po + pxs;
               asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
             }
           }
@@ -1032,7 +1041,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------ split-K finish
 // y = addend + alpha * act(inv_scale * sum_s ws[s] + bias): the partial sums are added in split order (deterministic).
 __global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_stride, int S, const uint8_t* __restrict__ wp,
-                                  const float* __restrict__ bias, HSegs seg, int Cout, int HWo, long long total) {
+                                  const float* __restrict__ bias, HSegs seg, int Cout, int HWo, int Wo, int Po, int Ho,
+                                  long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float inv_scale = __ldg(reinterpret_cast<const float*>(wp) + 1);
@@ -1048,7 +1058,8 @@ __global__ void h16_splitk_finish(const float* __restrict__ ws, long long ws_str
   for (int k = 1; k < H_MAXSEG; ++k)
     if (k < seg.n && c >= seg.s[k].n_begin) si = k;
   const HSeg& sg = seg.s[si];
-  const size_t o = (size_t)(c - sg.n_begin) * HWo + pix;
+  const int oy = pix / Wo;
+  const size_t o = (size_t)(c - sg.n_begin) * ((size_t)Ho * Po) + (size_t)oy * Po + (pix - oy * Wo);   // pitched rows
   const float add = sg.addend ? __ldg(sg.addend + (size_t)b * sg.a_bs + o) : 0.f;
   if (sg.pre) a += add;
   sg.y[(size_t)b * sg.y_bs + o] = fmaf(leaky(a, sg.slope), sg.alpha, sg.pre ? 0.f : add);
@@ -1204,7 +1215,8 @@ size_t h16_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks, int s
 }
 
 int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, const HSeg* segs, int nseg, int B, int Cin,
-             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st) {
+             int H, int W, int Cout, int ks, int stride, int dil, void* ws, size_t ws_bytes, cudaStream_t st, int pitch_in,
+             int pitch_out) {
   HGeom g = h_geom(Cout, Cin, ks);
   HArgs a;
   memset(&a, 0, sizeof(a));
@@ -1226,20 +1238,25 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   a.Wo = (W + 2 * a.pad - dil * (ks - 1) - 1) / stride + 1;
   a.n_tile = g.n_tile; a.n_tiles = g.n_tiles; a.cchunks = g.cchunks; a.nkb = g.nkb;
   a.M = (long long)B * a.Ho * a.Wo;
+  a.Pi = pitch_in > 0 ? pitch_in : W;
+  a.Po = pitch_out > 0 ? pitch_out : a.Wo;
+  if (a.Pi < W || a.Po < a.Wo) return fail_arg("irr_conv2d_fwd", "row pitch smaller than the width");
   const size_t misc = 56 * 8 + 256 * 4 + 64;
   const size_t total_b = (size_t)g.nkb * g.img_bytes;
 
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   EncodeTiledFn enc = encode_tiled();
-  const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
+  // TMA needs 16-byte aligned rows and planes: a row pitch that is a multiple of 4 gives that for ANY width (KITTI's
+  // 621 / 311 / 78 / 39 are stored with pitch 624 / 312 / 80 / 40); columns >= W are zero-filled by the tensor map.
+  const bool tma_ok = enc != nullptr && !force_gather() && stride == 1 && (a.Pi % 4) == 0 &&
                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
   // ---- rolling kernel: single-chunk thin layers on wide images
   if (tma_ok && !no_roll() && single && ks == 3 && dil == 1 && Cin <= H_CK && g.n_tiles == 1 && g.n_tile <= 32 && W >= 96) {
     RArgs r;
     memset(&r, 0, sizeof(r));
     r.x = x; r.x_bs = x_bs; r.wp = (const uint8_t*)w; r.bias = bias; r.addend = addend; r.a_bs = a_bs; r.y = y; r.y_bs = y_bs;
-    r.B = B; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.n_tile = g.n_tile;
+    r.B = B; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.n_tile = g.n_tile; r.Pi = a.Pi; r.Po = a.Po;
     r.slope = slope; r.alpha = alpha;
     { const char* e = getenv("IRR_ROLL_UNORDERED"); r.unordered = (e && e[0] == '1') ? 1 : 0; }
     r.xtiles = (W + 127) / 128;
@@ -1249,7 +1266,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
     r.segs = (H + L - 1) / L;
     r.items = B * r.xtiles * r.segs;
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)x_bs * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)a.Pi * 4, (cuuint64_t)H * a.Pi * 4, (cuuint64_t)x_bs * 4};
     cuuint32_t box[4] = {(cuuint32_t)R_PW, 1, (cuuint32_t)H_CK, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
@@ -1265,8 +1282,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
       return rc;
     }
   }
-  bool staged = enc != nullptr && !force_gather() && stride == 1 && (W % 4) == 0 &&
-                (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bs % 4) == 0 && a.Ho == H && a.Wo == W;
+  bool staged = tma_ok;
   if (staged) {
     // half = RH rows x RW columns, RW = smallest power of two >= W, clamped to [16, 128]
     int rwl, yt_, xt_;
@@ -1285,7 +1301,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   }
   if (staged) {
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)x_bs * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)a.Pi * 4, (cuuint64_t)H * a.Pi * 4, (cuuint64_t)x_bs * 4};
     cuuint32_t box[4] = {(cuuint32_t)a.PW, (cuuint32_t)a.R, (cuuint32_t)H_CK, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
@@ -1336,7 +1352,7 @@ int h16_conv(const float* x, long long x_bs, const void* w, const float* bias, c
   if (rc != 0 || a.ksplit == 1) return rc;
   const long long total = (long long)B * Cout * a.Ho * a.Wo;
   h16_splitk_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.ws, a.ws_stride, a.ksplit, a.wp, bias, a.seg, Cout,
-                                                                     a.Ho * a.Wo, total);
+                                                                     a.Ho * a.Wo, a.Wo, a.Po, a.Ho, total);
   return check_launch("irr_conv2d_fwd");
 }
 

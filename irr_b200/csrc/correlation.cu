@@ -118,11 +118,11 @@ template <int NS, bool PREFETCH, class Hook, bool SPLIT = false>
 __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem, uint32_t full0, uint32_t empty0,
                                              const float* __restrict__ f1, long long f1_bs,
                                              const float* __restrict__ f2, long long f2_bs, float* __restrict__ out,
-                                             long long out_bs, int B, int C, int H, int W, int shift, float slope,
+                                             long long out_bs, int B, int C, int H, int W, int P, int shift, float slope,
                                              int vec_ok, int tiles_x, int tiles_y, int ntiles, int ctr = 0,
                                              CSplit sp = CSplit{1, 0, nullptr, 0}) {
   const int tid = threadIdx.x;
-  const int HW = H * W;
+  const int HW = H * P;   // channel stride: rows are stored with pitch P >= W (include/irr_b200.h)
   const int nchunks = (C + CC - 1) / CC;
   const int ksplit = SPLIT ? sp.ksplit : 1;
   const int nvt = ntiles * ksplit;
@@ -188,12 +188,12 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
           const float* a;
           if (rr < 8) {
             const int y = min(ny0 + rr, H - 1);
-            a = pf1 + (size_t)c * HW + (size_t)y * W + min(nx0, W - 1);
+            a = pf1 + (size_t)c * HW + (size_t)y * P + min(nx0, W - 1);
           } else {
             const int k = rr - 8;
             const int y = min(max(ny0 - MD + (k >> 1), 0), H - 1);
             const int x = min(max(nx0 - MD + (k & 1) * 32, 0), W - 1);
-            a = pf2 + (size_t)c * HW + (size_t)y * W + x;
+            a = pf2 + (size_t)c * HW + (size_t)y * P + x;
           }
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
@@ -234,8 +234,8 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
     if (SPLIT) {
       // channel-split launch: raw partial sums of chunks [c_lo, c_hi) into this split's workspace slice
       if (pair_ok && gy < H && gx < W) {
-        float* op = sp.ws + (size_t)ks * sp.ws_stride + ((size_t)b * (ND * ND) + (size_t)(dyi * ND)) * HW + (size_t)gy * W + gx;
-        if ((W & 3) == 0 && gx + PX <= W) {
+        float* op = sp.ws + (size_t)ks * sp.ws_stride + ((size_t)b * (ND * ND) + (size_t)(dyi * ND)) * HW + (size_t)gy * P + gx;
+        if ((P & 3) == 0 && gx + PX <= W) {
 #pragma unroll
           for (int d = 0; d < ND; ++d) {
             float4* q = reinterpret_cast<float4*>(op + (size_t)d * HW);
@@ -252,7 +252,7 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
       }
     } else if (pair_ok && gy < H && gx < W) {
       const float inv_c = 1.0f / (float)C;  // mean over channels as one multiply (<= 1 ulp from the reference's divide)
-      float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * W + gx;
+      float* op = out + (size_t)b * out_bs + (size_t)(dyi * ND) * HW + (size_t)gy * P + gx;
       // scale in place first, then issue the stores back to back (a temporary per displacement makes every store
       // wait for the previous one to release its registers).  slope in [0, 1]: leaky(v) == max(v, v * slope).
       if (slope >= 0.f && slope <= 1.f) {
@@ -302,8 +302,8 @@ template <bool FUSED>
 __global__ void __launch_bounds__(CORR_THREADS, 1)
     corr_kernel(const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                 const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
-                GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int vec_in, int tiles_x, int tiles_y,
-                int ntiles) {
+                GridArgs g, int B, int C, int H, int W, int P, int shift, float slope, int vec_ok, int vec_in, int tiles_x,
+                int tiles_y, int ntiles) {
   extern __shared__ __align__(16) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CORR_STAGES * STAGE_ELEMS);
   const uint32_t bar0 = smem_u32(bars);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
   auto empty = [&](int s) { return bar0 + 8u * (CORR_STAGES + s); };
 
   const int tid = threadIdx.x;
-  const int HW = H * W;
+  const int HW = H * P;   // channel stride (pitched rows)
   const int nchunks = (C + CC - 1) / CC;
   if (tid == 0) {
     for (int s = 0; s < CORR_STAGES; ++s) {
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
           const int gy = y0 - MD + hr, gx = x0 - MD + hx;
           q.soff = F1_ELEMS + hr * F2_P + hx;
           if (FUSED && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * W + gx;
+            const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * P + gx;
             float ix, iy;
             sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
             Taps tp = make_taps(ix, iy, W, H);
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
               const int xa = min(max(tp.x0, 0), W - 1), xb = min(max(tp.x0 + 1, 0), W - 1);
               const int ya = min(max(tp.y0, 0), H - 1), yb = min(max(tp.y0 + 1, 0), H - 1);
               ya_[k] = ya; xa_[k] = xa;
-              q.goff = ya * W + xa;
+              q.goff = ya * P + xa;
               q.dx = (xb != xa) ? 1 : 0;
               q.dy = (yb != ya) ? 1 : 0;  // in rows; scaled by the row pitch of whichever source is sampled
               // a clamped (out-of-range) tap has zero weight (make_taps), so aliasing it onto its in-range neighbour's
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
             const int xq = j & 7, rr = (j >> 3) & 7, cc = j >> 6;
             const int gy = y0 + rr, gx = x0 + xq * 4, c = c0 + cc;
             const bool ok = c < C && gy < H && gx < W;
-            cp_async16(smem_u32(st + (cc * TH + rr) * F1_P + xq * 4), ok ? f1b + (size_t)c * HW + (size_t)gy * W + gx : f1b, ok);
+            cp_async16(smem_u32(st + (cc * TH + rr) * F1_P + xq * 4), ok ? f1b + (size_t)c * HW + (size_t)gy * P + gx : f1b, ok);
           }
           if (!FUSED) {
             for (int j = pt; j < CC * F2_H * (F2_WV / 4); j += NPROD) {  // f2 halo: 8 ch x 16 rows x 10 float4
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
               const int hr = r2 / 10, xq = r2 - hr * 10;
               const int gy = y0 - MD + hr, gx = x0 - MD + xq * 4, c = c0 + cc;
               const bool ok = c < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
-              cp_async16(smem_u32(st + F1_ELEMS + (cc * F2_H + hr) * F2_P + xq * 4), ok ? f2b + (size_t)c * HW + (size_t)gy * W + gx : f2b, ok);
+              cp_async16(smem_u32(st + F1_ELEMS + (cc * F2_H + hr) * F2_P + xq * 4), ok ? f2b + (size_t)c * HW + (size_t)gy * P + gx : f2b, ok);
             }
           } else if (foot) {
             float* fp = fpr + s * FP_ELEMS;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
               const int fr = r2 / (FP_W / 4), xq = r2 - fr * (FP_W / 4);
               const int gy = oy + fr, gx = ox + xq * 4, c = c0 + cc;
               const bool ok = c < C && gy < H && gx < W;  // oy, ox >= 0
-              cp_async16(smem_u32(fp + (cc * FP_H + fr) * FP_W + xq * 4), ok ? f2b + (size_t)c * HW + (size_t)gy * W + gx : f2b, ok);
+              cp_async16(smem_u32(fp + (cc * FP_H + fr) * FP_W + xq * 4), ok ? f2b + (size_t)c * HW + (size_t)gy * P + gx : f2b, ok);
             }
           }
         } else {
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
             const int xx = j & 31, rr = (j >> 5) & 7, cc = j >> 8;
             const int gy = y0 + rr, gx = x0 + xx, c = c0 + cc;
             const bool ok = c < C && gy < H && gx < W;
-            cp_async4(smem_u32(st + (cc * TH + rr) * F1_P + xx), ok ? f1b + (size_t)c * HW + (size_t)gy * W + gx : f1b, ok);
+            cp_async4(smem_u32(st + (cc * TH + rr) * F1_P + xx), ok ? f1b + (size_t)c * HW + (size_t)gy * P + gx : f1b, ok);
           }
           if (!FUSED) {
             for (int j = pt; j < CC * NHALO; j += NPROD) {
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
               const int hr = h2 / F2_WV, hx = h2 - hr * F2_WV;
               const int gy = y0 - MD + hr, gx = x0 - MD + hx, c = c0 + cc;
               const bool ok = c < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
-              cp_async4(smem_u32(st + F1_ELEMS + (cc * F2_H + hr) * F2_P + hx), ok ? f2b + (size_t)c * HW + (size_t)gy * W + gx : f2b, ok);
+              cp_async4(smem_u32(st + F1_ELEMS + (cc * F2_H + hr) * F2_P + hx), ok ? f2b + (size_t)c * HW + (size_t)gy * P + gx : f2b, ok);
             }
           }
         }
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
               if (hp[k].soff >= 0) {
                 const bool live = hp[k].w00 != 0.f || hp[k].w01 != 0.f || hp[k].w10 != 0.f || hp[k].w11 != 0.f;
                 const float* p = f2b + (size_t)c0 * HW + hp[k].goff;
-                const int dx = hp[k].dx, dy = hp[k].dy * W;
+                const int dx = hp[k].dx, dy = hp[k].dy * P;
                 float t[4][CC];
 #pragma unroll
                 for (int cc = 0; cc < CC; ++cc) {
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 1)
       gchunk += nchunks;
     }
   } else {
-    corr_compute<CORR_STAGES, true>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, shift, slope,
+    corr_compute<CORR_STAGES, true>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W, P, shift, slope,
                                     vec_ok, tiles_x, tiles_y, ntiles);
   }
 }
@@ -560,14 +560,14 @@ constexpr int CORR_SMEM_TMA_FUSED = T_NS_FUSED * STAGE_ELEMS * 4 + T_NFS * FP_EL
 struct TapSetup {
   const float* flow; long long flow_bs;
   GridArgs g;
-  int H, W, tiles_x, tiles_y;
+  int H, W, P, tiles_x, tiles_y;
   float* tab;      // [2][T_TAB_WORDS]
   int* meta;       // [2][4] {oy, ox, foot, -}
   int* red;        // [3][4] {ymin, ymax, xmin, xmax}
   uint32_t tabfull0;
   __device__ __forceinline__ void setup(int tile, int j) const {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int HW = H * W;
+    const int HW = H * P;
     const int tx = tile % tiles_x;
     const int ty = (tile / tiles_x) % tiles_y;
     const int b = tile / (tiles_x * tiles_y);
@@ -586,7 +586,7 @@ struct TapSetup {
       const int hr = h / F2_WV, hx = h - hr * F2_WV;
       const int gy = y0 - MD + hr, gx = x0 - MD + hx;
       in_[k] = h < NHALO && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      const float* fl = flow + (size_t)b * flow_bs + (in_[k] ? (size_t)gy * W + gx : 0);
+      const float* fl = flow + (size_t)b * flow_bs + (in_[k] ? (size_t)gy * P + gx : 0);
       fu[k] = __ldg(fl); fv[k] = __ldg(fl + HW);
     }
     float4 wq[T_KSET];
@@ -634,7 +634,7 @@ struct TapSetup {
       const int h = tid + k * NCOMP;
       if (h < NHALO) {
         tw[h] = wq[k];
-        const int off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * W + xa_[k];
+        const int off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * P + xa_[k];
         to[h] = dxy[k] < 0 ? -1 : ((off << 2) | dxy[k]);
       }
     }
@@ -654,15 +654,15 @@ struct TapSetup {
 // one int  (ya << 16) | (xa << 2) | dxy  (dxy bit 0 / 1: the second column / row is a distinct in-range texel), -1 = the
 // pixel samples nothing (masked out or fully out of bounds).  Needs H < 32768 and W < 16384.
 __global__ void __launch_bounds__(256) corr_taps_kernel(const float* __restrict__ flow, long long flow_bs, GridArgs g, int H,
-                                                        int W, float4* __restrict__ tabW, int* __restrict__ tabI) {
+                                                        int W, int P, float4* __restrict__ tabW, int* __restrict__ tabI) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = H * W;
   if (pix >= HW) return;
   const int b = blockIdx.y;
   const int gy = pix / W, gx = pix - gy * W;
-  const float* fl = flow + (size_t)b * flow_bs + pix;
+  const float* fl = flow + (size_t)b * flow_bs + (size_t)gy * P + gx;
   float ix, iy;
-  sample_coords(g, __ldg(fl), __ldg(fl + HW), gx, gy, W, H, ix, iy);
+  sample_coords(g, __ldg(fl), __ldg(fl + (size_t)H * P), gx, gy, W, H, ix, iy);
   const Taps tp = make_taps(ix, iy, W, H);
   float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
   int e = -1;
@@ -681,8 +681,9 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     corr_tma_kernel(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                     const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                     const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
-                    GridArgs g, int B, int C, int H, int W, int shift, float slope, int vec_ok, int tiles_x, int tiles_y,
-                    int ntiles, int ctr, CSplit sp, const float4* __restrict__ tabW, const int* __restrict__ tabI) {
+                    GridArgs g, int B, int C, int H, int W, int P, int shift, float slope, int vec_ok, int tiles_x,
+                    int tiles_y, int ntiles, int ctr, CSplit sp, const float4* __restrict__ tabW,
+                    const int* __restrict__ tabI) {
   constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
   const int ksplit = SPLIT ? sp.ksplit : 1;
   const int nvt = ntiles * ksplit;
@@ -701,7 +702,8 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
   int* red = meta + 8;
 
   const int tid = threadIdx.x;
-  const int HW = H * W;
+  const int HW = H * P;    // channel stride (pitched rows)
+  const int HWd = H * W;   // dense: the pre-pass' tap table
   const int nchunks = (C + CC - 1) / CC;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -724,13 +726,13 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
   if (tid < NCOMP) {
     if (FUSED && !PRETAB) {
       TapSetup hook;
-      hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.tiles_x = tiles_x;
+      hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.P = P; hook.tiles_x = tiles_x;
       hook.tiles_y = tiles_y; hook.tab = tab; hook.meta = meta; hook.red = red; hook.tabfull0 = tabfull(0);
       corr_compute<NS, false, TapSetup, SPLIT>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W,
-                                               shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
+                                               P, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
     } else {
       corr_compute<NS, false, NoTileHook, SPLIT>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B,
-                                                 C, H, W, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
+                                                 C, H, W, P, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
     }
   } else if (FUSED && PRETAB && (tid >> 5) == (T_ISSUER_FUSED >> 5)) {
     // ============================== COPY ISSUER, table from the pre-pass (one warp) ==============================
@@ -747,7 +749,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       const int b = tile / (tiles_x * tiles_y);
       const int y0 = ty * TH, x0 = tx * TW;
       int lo_y = 1 << 30, hi_y = -1, lo_x = 1 << 30, hi_x = -1;
-      const int* tI = tabI + (size_t)b * HW;
+      const int* tI = tabI + (size_t)b * HWd;
       int e[(NHALO + 31) / 32];
 #pragma unroll
       for (int k = 0; k < (NHALO + 31) / 32; ++k) {   // all loads in flight first
@@ -878,8 +880,8 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       const int ty = (tl / tiles_x) % tiles_y;
       const int tb = tl / (tiles_x * tiles_y);
       const int y0 = ty * TH, x0 = tx * TW;
-      const float4* tW = tabW + (size_t)tb * HW;
-      const int* tI = tabI + (size_t)tb * HW;
+      const float4* tW = tabW + (size_t)tb * HWd;
+      const int* tI = tabI + (size_t)tb * HWd;
 #pragma unroll
       for (int k = 0; k < T_KPOS; ++k) {
         const int h = pt + k * T_NSAMP;
@@ -914,7 +916,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
           od[k] = -1;
           if (pre_e[k] >= 0) {
             const int ya = pre_e[k] >> 16, xa = (pre_e[k] >> 2) & 0x3fff;
-            const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * W + xa;
+            const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * P + xa;
             od[k] = (off << 2) | (pre_e[k] & 3);
             wq[k] = pre_w[k];
           }
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
               float* dst = st + hr * F2_P + hx;
               const bool live = od[k] >= 0;
               const float* pq = f2b + (size_t)c0 * HW + (live ? (od[k] >> 2) : 0);
-              const int dx = live ? (od[k] & 1) : 0, dy = (live && (od[k] & 2)) ? W : 0;
+              const int dx = live ? (od[k] & 1) : 0, dy = (live && (od[k] & 2)) ? P : 0;
               float t[4][CC];
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
@@ -1088,7 +1090,7 @@ size_t corr_workspace_bytes(int B, int C, int H, int W, int fused) {
   if (nt > 0x7fffffffLL) return 0;
   int cps;
   const int k = corr_ksplit((int)nt, (C + CC - 1) / CC, &cps);
-  size_t n = k > 1 ? (size_t)k * B * (ND * ND) * H * W * sizeof(float) : 0;
+  size_t n = k > 1 ? (size_t)k * B * (ND * ND) * H * ((W + 3) & ~3) * sizeof(float) : 0;
   if (fused && !corr_no_pretab() && H < 32768 && W < 16384) n += corr_tab_bytes(B, H, W);
   return n;
 }
@@ -1106,15 +1108,20 @@ static bool corr_ctr_on() {  // IRR_CORR_CTR=1: role cycle counters (debug)
 template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
-                       int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+                       int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st,
+                       int pitch = 0) {
   constexpr int CORR_SMEM = FUSED ? CORR_SMEM_FUSED : CORR_SMEM_PLAIN;
   static SmemAttrCache attr = {};
   if (int rc = ensure_dyn_smem(corr_kernel<FUSED>, CORR_SMEM, attr, fn)) return rc;
-  int vec_ok = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (vec_ok && (W % 8 == 0) && (((long long)H * W) % 8 == 0) && (out_bs % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0))
+  // every H x W tensor of the call (f1, f2, flow, out) is stored with row pitch P >= W; P % 4 == 0 puts any width on the
+  // TMA / vector paths (the tensor maps zero-fill columns >= W)
+  const int P = pitch > 0 ? pitch : W;
+  if (P < W) return fail_arg(fn, "row pitch smaller than the width");
+  int vec_ok = (P % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec_ok && (P % 8 == 0) && (((long long)H * P) % 8 == 0) && (out_bs % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0))
     vec_ok = 2;  // every 8-pixel strip of every output plane is 32-byte aligned
   // 16-byte cp.async staging needs 16-byte aligned rows in both operands
-  int vec_in = (W % 4 == 0) && (f1_bs % 4 == 0) && (f2_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15) == 0) &&
+  int vec_in = (P % 4 == 0) && (f1_bs % 4 == 0) && (f2_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(f2) & 15) == 0);
   int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   long long nt = (long long)tiles_x * tiles_y * B;
@@ -1125,8 +1132,8 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
     constexpr int TSMEM = FUSED ? CORR_SMEM_TMA_FUSED : CORR_SMEM_TMA_PLAIN;
     static SmemAttrCache tattr = {}, tattr_split = {}, tattr_pre = {}, tattr_pre_split = {};
     CUtensorMap m1, m2;
-    if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC) &&
-        make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC)) {
+    if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC, P) &&
+        make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC, P)) {
       const int ctr = corr_ctr_on() ? 1 : 0;
       if (ctr) {
         static const unsigned long long zeros[32] = {0};
@@ -1146,13 +1153,13 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
         wsp += corr_tab_bytes(B, H, W);
         ws_left -= corr_tab_bytes(B, H, W);
         dim3 pg((unsigned)((H * W + 255) / 256), (unsigned)B);
-        corr_taps_kernel<<<pg, 256, 0, st>>>(flow, flow_bs, g, H, W, tabW, tabI);
+        corr_taps_kernel<<<pg, 256, 0, st>>>(flow, flow_bs, g, H, W, P, tabW, tabI);
         if (int rc = check_launch(fn)) return rc;
       }
       if (wsp != nullptr && !corr_no_split() && (reinterpret_cast<uintptr_t>(wsp) & 15) == 0) {
         int cps;
         const int k = corr_ksplit(ntiles, (C + CC - 1) / CC, &cps);
-        const size_t slice = (size_t)B * (ND * ND) * H * W;
+        const size_t slice = (size_t)B * (ND * ND) * H * P;   // the partial-sum slices are pitched like `out`
         if (k > 1 && (size_t)k * slice * sizeof(float) <= ws_left) {
           sp.ksplit = k; sp.cps = cps; sp.ws = reinterpret_cast<float*>(wsp); sp.ws_stride = (long long)slice;
           const long long nvt = (long long)ntiles * k;
@@ -1164,8 +1171,8 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   do {                                                                                                                     \
     if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, SPLIT_, PRE_>, TSMEM, CACHE_, fn)) return rc;                       \
     corr_tma_kernel<FUSED, SPLIT_, PRE_><<<grid, nthr, TSMEM, st>>>(m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, \
-                                                                   g, B, C, H, W, shift, slope, vec_ok, tiles_x, tiles_y,  \
-                                                                   ntiles, ctr, sp, tabW, tabI);                           \
+                                                                   g, B, C, H, W, P, shift, slope, vec_ok, tiles_x,       \
+                                                                   tiles_y, ntiles, ctr, sp, tabW, tabI);                  \
   } while (0)
       if (FUSED && tabW != nullptr) {
         if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, FUSED, tattr_pre_split);
@@ -1177,8 +1184,8 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
 #undef IRR_CORR_LAUNCH
       if (int rc = check_launch(fn)) return rc;
       if (sp.ksplit > 1) {
-        const long long total = (long long)B * (ND * ND) * H * W;
-        corr_split_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sp.ws, sp.ws_stride, sp.ksplit, out, out_bs, H * W,
+        const long long total = (long long)B * (ND * ND) * H * P;
+        corr_split_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sp.ws, sp.ws_stride, sp.ksplit, out, out_bs, H * P,
                                                                           total, 1.0f / (float)C, slope);
         return check_launch(fn);
       }
@@ -1186,15 +1193,17 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
     }
   }
   corr_kernel<FUSED><<<grid, CORR_THREADS, CORR_SMEM, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H,
-                                                            W, shift, slope, vec_ok, vec_in, tiles_x, tiles_y, ntiles);
+                                                            W, P, shift, slope, vec_ok, vec_in, tiles_x, tiles_y, ntiles);
   return check_launch(fn);
 }
 
 // The fused launcher under a plain name, so the other translation unit (7-row tiles) can be called from this one.
 int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                               const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
-                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
-  return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, ws, ws_bytes, st);
+                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st,
+                              int pitch) {
+  return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, shift, slope, ws, ws_bytes, st,
+                           pitch);
 }
 
 }  // namespace IRR_CORR_NS
@@ -1205,7 +1214,8 @@ namespace irr {
 namespace corr7 {   // correlation7.cu: 7-row tiles
 int launch_corr_fused_variant(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                               const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
-                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+                              int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st,
+                              int pitch);
 size_t corr_workspace_bytes(int B, int C, int H, int W, int fused);
 }  // namespace corr7
 }  // namespace irr
@@ -1246,7 +1256,7 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
                                 long long flow_bs, const float* lin_x, const float* lin_y, float* out, long long out_bs,
                                 int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
                                 int f2_batch_shift, float leaky_slope, int grid_flags, void* workspace,
-                                size_t workspace_bytes, irr_stream_t stream) {
+                                size_t workspace_bytes, int pitch, irr_stream_t stream) {
   const char* fn = "irr_warp_correlation_fwd_ws";
   IRR_REQUIRE(f1 && f2 && out, fn, "null pointer");
   IRR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, fn, "non-positive size");
@@ -1255,15 +1265,15 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
   if (flow == nullptr) {  // no warp: the plain cost volume
     GridArgs g = make_grid_args(nullptr, nullptr, H, W, H, W, 1.f, 0);
     return launch_corr<false>(fn, f1, f1_bs, f2, f2_bs, nullptr, 0, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
-                              workspace, workspace_bytes, as_stream(stream));
+                              workspace, workspace_bytes, as_stream(stream), pitch);
   }
   IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
   if (!corr_force_th8())   // experimental: 7-row tiles, 8 compute warps, two per scheduler (correlation7.cu)
     return corr7::launch_corr_fused_variant(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W,
-                                            f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream));
+                                            f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream), pitch);
   return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
-                           workspace, workspace_bytes, as_stream(stream));
+                           workspace, workspace_bytes, as_stream(stream), pitch);
 }
 
 int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,

@@ -40,8 +40,9 @@ class OccUpsampleNetwork(nn.Module):
         return self.out_convs(x_init2, addend=x_in[:, 0:1])
 
     def forward(self, occ, x):
+        occ, x = ops.pitched(occ), ops.pitched(x)
         B, C, H, W = x.shape
-        x_in = torch.empty((B, C + 1, H, W), dtype=torch.float32, device=x.device)
+        x_in = ops.empty(B, C + 1, H, W, x.device)
         ops.upsample_nearest2x(occ, H, W, out=x_in[:, 0:1])
         ops.scale_channels(x, out=x_in[:, 1:])
         return self.forward_into(x_in)
@@ -74,8 +75,9 @@ class RefineFlow(_Refine):
     """models/irr_modules.py:63-104."""
 
     def forward(self, flow, diff_img, feature):
+        flow, diff_img, feature = ops.pitched(flow), ops.pitched(diff_img), ops.pitched(feature)
         B, _, H, W = flow.shape
-        x_in = torch.empty((B, self.ch_in, H, W), dtype=torch.float32, device=flow.device)
+        x_in = ops.empty(B, self.ch_in, H, W, flow.device)
         ops.sub_spatial_mean(flow, out=x_in[:, 0:2])
         ops.channel_l2norm(diff_img, out=x_in[:, 2:3])
         ops.scale_channels(feature, out=x_in[:, 3:])
@@ -86,9 +88,10 @@ class RefineOcc(_Refine):
     """models/irr_modules.py:107-138."""
 
     def forward(self, occ, feat1, feat2):
+        occ, feat1, feat2 = ops.pitched(occ), ops.pitched(feat1), ops.pitched(feat2)
         B, _, H, W = occ.shape
         c1 = feat1.shape[1]
-        x_in = torch.empty((B, self.ch_in, H, W), dtype=torch.float32, device=occ.device)
+        x_in = ops.empty(B, self.ch_in, H, W, occ.device)
         ops.scale_channels(occ, out=x_in[:, 0:1])
         ops.scale_channels(feat1, out=x_in[:, 1:1 + c1])
         ops.scale_channels(feat2, out=x_in[:, 1 + c1:])

@@ -60,17 +60,100 @@ def _launch(what: str, meta, fn, *args) -> None:
     _lib.check(rc, what)
 
 
-def _v(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int]:
-    """(data_ptr, batch_stride_in_elements) of an NCHW channel-slice view."""
+def _vp(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int, int]:
+    """(data_ptr, batch_stride, row_pitch) in elements of an NCHW channel-slice view whose rows may be stored with a
+    pitch P >= W (``buf[:, a:b, :, :W]`` of a ``(B, C, H, P)`` buffer: stride(2) = P, stride(1) = H*P) — include/irr_b200.h,
+    "ROW PITCH"."""
     if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
         raise RuntimeError(f"irr_b200: {name} must be a 4-D fp32 CUDA tensor (got {t.dtype}, {t.device}, dim {t.dim()})")
     B, Cc, H, W = t.shape
     s = t.stride()
-    ok = (W == 1 or s[3] == 1) and (H == 1 or s[2] == W) and (Cc == 1 or s[1] == H * W)
+    # a single row of a single channel has no pitch: 0 = "any" (callers merge it with the other operands' pitch)
+    P = s[2] if H > 1 else (s[1] if Cc > 1 else 0)
+    ok = (W == 1 or s[3] == 1) and (P == 0 or P >= W) and (Cc == 1 or s[1] == H * P)
     if not ok:
         raise RuntimeError(f"irr_b200: {name} is not an NCHW channel-slice view (shape {tuple(t.shape)}, strides {s})")
-    bs = s[0] if B > 1 else Cc * H * W
-    return t.data_ptr(), bs
+    bs = s[0] if B > 1 else Cc * H * (P or W)
+    return t.data_ptr(), bs, P
+
+
+def _v(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int]:
+    """(data_ptr, batch_stride_in_elements) of a DENSE NCHW channel-slice view (row pitch == W)."""
+    ptr, bs, P = _vp(t, name)
+    if P and P != t.shape[3]:
+        raise RuntimeError(f"irr_b200: {name} must have dense rows here (width {t.shape[3]}, row pitch {P})")
+    return ptr, bs
+
+
+def _pitch(name: str, *ps: int) -> int:
+    """The common row pitch of the same-sized tensors of one call (0 = no operand has one: dense)."""
+    nz = [p for p in ps if p]
+    if any(p != nz[0] for p in nz):
+        raise RuntimeError(f"irr_b200.{name}: tensors of one spatial size must share the row pitch (got {ps})")
+    return nz[0] if nz else 0
+
+
+def _is_pitched(t: torch.Tensor) -> Optional[bool]:
+    """True / False: ``t`` has padded / dense rows; None: it has no pitch (one row of one channel) -> module default."""
+    P = _vp(t)[2]
+    return (P != t.shape[3]) if P else None
+
+
+# Row pitch of the buffers this module and the model classes allocate: widths that are not a multiple of 4 (KITTI's
+# 621 / 311 / 78 / 39 ...) are stored with the next multiple of 4 as row pitch, which puts them on the TMA paths of the
+# conv and correlation kernels.  Only the 3xF16 conv path understands pitched tensors, so pwc_modules.set_conv_math()
+# switches this off for the other math modes.
+PITCH_ALIGN = 4
+_pitch_enabled = True
+
+
+def set_pitch_enabled(flag: bool) -> None:
+    global _pitch_enabled
+    _pitch_enabled = bool(flag)
+
+
+def empty(B: int, C: int, H: int, W: int, device, pitched: Optional[bool] = None, zero: bool = False) -> torch.Tensor:
+    """A (B, C, H, W) fp32 tensor; when ``W`` is not a multiple of PITCH_ALIGN (and pitching is on) it is the ``[..., :W]``
+    view of a buffer whose rows are padded to the next multiple (the pad columns are never read)."""
+    use = _pitch_enabled if pitched is None else pitched
+    Pw = (W + PITCH_ALIGN - 1) // PITCH_ALIGN * PITCH_ALIGN if use else W
+    f = torch.zeros if zero else torch.empty
+    t = f((B, C, H, Pw), dtype=torch.float32, device=device)
+    return t if Pw == W else t[:, :, :, :W]
+
+
+def new_like(ref: torch.Tensor, C: int, zero: bool = False) -> torch.Tensor:
+    """A (B, C, H, W) tensor with the batch, spatial size, device and row pitch of ``ref``."""
+    B, _, H, W = ref.shape
+    return empty(B, C, H, W, ref.device, pitched=_is_pitched(ref), zero=zero)
+
+
+def pitched(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """``t`` in the row pitch this module allocates with: unchanged when it already has it (always the case inside a
+    model's forward), else a pitched copy (stage-level entry points fed with dense tensors)."""
+    if t is None:
+        return None
+    B, C, H, W = t.shape
+    want = (W + PITCH_ALIGN - 1) // PITCH_ALIGN * PITCH_ALIGN if _pitch_enabled else W
+    if t.is_cuda and t.dtype == torch.float32 and t.dim() == 4:
+        s = t.stride()
+        if (W == 1 or s[3] == 1) and (H == 1 or s[2] == want) and (C == 1 or s[1] == H * want):
+            return t
+    return scale_channels(t.contiguous().float(), out=empty(B, C, H, W, t.device))
+
+
+def stack_pair(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """torch.cat([x1, x2], 0) into a (possibly row-pitched) fp32 buffer — the only data movement done by torch."""
+    B, C, H, W = x1.shape
+    t = empty(2 * B, C, H, W, x1.device)
+    t[:B].copy_(x1)
+    t[B:].copy_(x2)
+    return t
+
+
+def flat_hw(t: torch.Tensor) -> int:
+    """H * row_pitch: the per-channel element count the flat kernels (scale / round / l2norm) iterate over."""
+    return t.shape[2] * (_vp(t)[2] or t.shape[3])
 
 
 def _p(t: torch.Tensor, name: str, like: Optional[torch.Tensor] = None, numel: Optional[int] = None) -> int:
@@ -100,8 +183,8 @@ def host_linspace(n: int, device) -> torch.Tensor:
     return t
 
 
-def _new(like: torch.Tensor, C: int, H: int, W: int) -> torch.Tensor:
-    return torch.empty((like.shape[0], C, H, W), dtype=torch.float32, device=like.device)
+def _new(like: torch.Tensor, C: int, H: int, W: int, pitched: Optional[bool] = None) -> torch.Tensor:
+    return empty(like.shape[0], C, H, W, like.device, pitched=pitched)
 
 
 _corr_ws_bytes = {}
@@ -123,16 +206,14 @@ def correlation(f1, f2, out=None, shift: int = 0, slope: float = 1.0, max_disp: 
     assert f2.shape == f1.shape
     D = (2 * max_disp + 1) ** 2
     if out is None:
-        out = _new(f1, D, H, W)
+        out = _new(f1, D, H, W, pitched=_is_pitched(f1))
     assert out.shape == (B, D, H, W)
-    p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); po, so = _v(out, "out")
+    p1, s1, q1 = _vp(f1, "f1"); p2, s2, q2 = _vp(f2, "f2"); po, so, qo = _vp(out, "out")
+    P = _pitch("correlation", q1, q2, qo)
     ws, nws = _corr_workspace(B, C, H, W, f1.device)
-    if ws is None:
-        _launch("correlation", (B, C, H, W), _lib.load().irr_correlation_fwd, p1, s1, p2, s2, po, so, B, C, H, W, max_disp,
-                shift, slope, _stream())
-    else:
-        _launch("correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, None, 0, None, None,
-                po, so, B, C, H, W, H, W, 1.0, max_disp, shift, slope, 0, ws.data_ptr(), nws, _stream())
+    _launch("correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, None, 0, None, None,
+            po, so, B, C, H, W, H, W, 1.0, max_disp, shift, slope, 0, ws.data_ptr() if ws is not None else None, nws, P,
+            _stream())
     return out
 
 
@@ -142,14 +223,15 @@ def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: floa
     assert f2.shape == f1.shape and flow.shape == (B, 2, H, W)
     D = (2 * max_disp + 1) ** 2
     if out is None:
-        out = _new(f1, D, H, W)
+        out = _new(f1, D, H, W, pitched=_is_pitched(f1))
     lx = host_linspace(W, f1.device) if lin_x is None else lin_x
     ly = host_linspace(H, f1.device) if lin_y is None else lin_y
-    p1, s1 = _v(f1, "f1"); p2, s2 = _v(f2, "f2"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
+    p1, s1, q1 = _vp(f1, "f1"); p2, s2, q2 = _vp(f2, "f2"); pf, sf, qf = _vp(flow, "flow"); po, so, qo = _vp(out, "out")
+    P = _pitch("warp_correlation", q1, q2, qf, qo)
     ws, nws = _corr_workspace(B, C, H, W, f1.device, fused=True)
     _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, pf, sf,
             _p(lx, "lin_x", f1, W), _p(ly, "lin_y", f1, H), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp,
-            shift, slope, _grid_mode, ws.data_ptr() if ws is not None else None, nws, _stream())
+            shift, slope, _grid_mode, ws.data_ptr() if ws is not None else None, nws, P, _stream())
     return out
 
 
@@ -158,14 +240,15 @@ def warp(x, flow, height_im: int, width_im: int, div_flow: float, out=None, minu
     B, C, H, W = x.shape
     assert flow.shape == (B, 2, H, W)
     if out is None:
-        out = _new(x, C, H, W)
+        out = _new(x, C, H, W, pitched=_is_pitched(x))
     lx = host_linspace(W, x.device) if lin_x is None else lin_x
     ly = host_linspace(H, x.device) if lin_y is None else lin_y
-    px, sx = _v(x, "x"); pf, sf = _v(flow, "flow"); po, so = _v(out, "out")
-    pm, sm = (_v(minuend, "minuend") if minuend is not None else (None, 0))
+    px, sx, qx = _vp(x, "x"); pf, sf, qf = _vp(flow, "flow"); po, so, qo = _vp(out, "out")
+    pm, sm, qm = (_vp(minuend, "minuend") if minuend is not None else (None, 0, qx))
+    P = _pitch("warp", qx, qf, qo, qm)
     _launch("warp", (B, C, H, W), _lib.load().irr_warp_fwd, px, sx, pf, sf, _p(lx, "lin_x", x, W), _p(ly, "lin_y", x, H),
             pm, sm, po, so, _p(mask_out, "mask_out", x, B * H * W) if mask_out is not None else None, B, C, H, W,
-            height_im, width_im, div_flow, shift, _grid_mode, _stream())
+            height_im, width_im, div_flow, shift, _grid_mode, P, _stream())
     return out
 
 
@@ -231,28 +314,33 @@ def pack_weights(w: torch.Tensor, math: int = MATH_FP32_SIMT) -> torch.Tensor:
 _ws_bytes = {}
 
 
-def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, slope: float = 0.1, out=None,
-           addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT):
-    B, Cin, H, W = x.shape
-    Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
-    if out is None:
-        out = _new(x, Cout, Ho, Wo)
-    assert out.shape == (B, Cout, Ho, Wo), (out.shape, (B, Cout, Ho, Wo))
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    pa, sa = (_v(addend, "addend") if addend is not None else (None, 0))
-    if addend is not None:
-        assert addend.shape == out.shape
-    lib = _lib.load()
-    # split-K scratch for layers with far fewer tiles than SMs (coarse pyramid levels); 0 bytes = never split
+def _conv_ws(lib, x, B, Cin, H, W, Cout, ks, stride, dil, math):
+    """split-K scratch for layers with far fewer tiles than SMs (coarse pyramid levels); 0 bytes = never split"""
     key = (B, Cin, H, W, Cout, ks, stride, dil, math)
     nws = _ws_bytes.get(key)
     if nws is None:
         nws = lib.irr_conv2d_workspace_bytes(B, Cin, H, W, Cout, ks, stride, dil, math)
         _ws_bytes[key] = nws
-    ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
+    return (torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None), nws
+
+
+def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, slope: float = 0.1, out=None,
+           addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT):
+    B, Cin, H, W = x.shape
+    Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
+    if out is None:   # only the 3xF16 path understands pitched rows
+        out = _new(x, Cout, Ho, Wo, pitched=(_pitch_enabled and math == MATH_TC_3XF16))
+    assert out.shape == (B, Cout, Ho, Wo), (out.shape, (B, Cout, Ho, Wo))
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    pa, sa, qa = (_vp(addend, "addend") if addend is not None else (None, 0, qo))
+    if addend is not None:
+        assert addend.shape == out.shape
+    qo = _pitch("conv2d", qo, qa)
+    lib = _lib.load()
+    ws, nws = _conv_ws(lib, x, B, Cin, H, W, Cout, ks, stride, dil, math)
     _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_ws, px, sx,
             _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, math,
-            ws.data_ptr() if ws is not None else None, nws, _stream())
+            ws.data_ptr() if ws is not None else None, nws, qx, qo, _stream())
     return out
 
 
@@ -264,19 +352,15 @@ def conv2d_dual(x, packed, bias, Cout: int, n_split: int, ks: int, out, out2, st
     B, Cin, H, W = x.shape
     Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
     assert out.shape == (B, n_split, Ho, Wo) and out2.shape == (B, Cout - n_split, Ho, Wo)
-    px, sx = _v(x, "x"); po, so = _v(out, "out"); po2, so2 = _v(out2, "out2")
-    pa, sa = (_v(addend, "addend") if addend is not None else (None, 0))
-    pa2, sa2 = (_v(addend2, "addend2") if addend2 is not None else (None, 0))
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out"); po2, so2, qo2 = _vp(out2, "out2")
+    pa, sa, qa = (_vp(addend, "addend") if addend is not None else (None, 0, qo))
+    pa2, sa2, qa2 = (_vp(addend2, "addend2") if addend2 is not None else (None, 0, qo))
+    qo = _pitch("conv2d_dual", qo, qo2, qa, qa2)
     lib = _lib.load()
-    key = (B, Cin, H, W, Cout, ks, stride, dil, math)
-    nws = _ws_bytes.get(key)
-    if nws is None:
-        nws = lib.irr_conv2d_workspace_bytes(B, Cin, H, W, Cout, ks, stride, dil, math)
-        _ws_bytes[key] = nws
-    ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
+    ws, nws = _conv_ws(lib, x, B, Cin, H, W, Cout, ks, stride, dil, math)
     _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_dual, px, sx,
             _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), pa, sa, po, so, B, Cin, H, W, Cout, ks, stride, dil, slope, alpha, n_split,
-            pa2, sa2, po2, so2, slope2, alpha2, math, ws.data_ptr() if ws is not None else None, nws, _stream())
+            pa2, sa2, po2, so2, slope2, alpha2, math, ws.data_ptr() if ws is not None else None, nws, qx, qo, _stream())
     return out, out2
 
 
@@ -287,48 +371,51 @@ def conv2d_multi(x, packed, bias, Cout: int, ks: int, segs, stride: int = 1, dil
     [n_begin_i, n_begin_{i+1}) and ``out`` must have exactly that many channels."""
     B, Cin, H, W = x.shape
     Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
-    px, sx = _v(x, "x")
+    px, sx, qx = _vp(x, "x")
     arr = (_lib.ConvSeg * len(segs))()
+    qs = []
     for i, sg in enumerate(segs):
         n_end = segs[i + 1]["n_begin"] if i + 1 < len(segs) else Cout
         out = sg["out"]
         assert out.shape == (B, n_end - sg["n_begin"], Ho, Wo), (tuple(out.shape), (B, n_end - sg["n_begin"], Ho, Wo))
-        po, so = _v(out, f"out[{i}]")
+        po, so, qo = _vp(out, f"out[{i}]")
+        qs.append(qo)
         add = sg.get("addend")
         if add is not None:
             assert add.shape == out.shape
-        pa, sa = (_v(add, f"addend[{i}]") if add is not None else (None, 0))
+        pa, sa, qa = (_vp(add, f"addend[{i}]") if add is not None else (None, 0, qo))
+        qs.append(qa)
         arr[i].n_begin = sg["n_begin"]; arr[i].addend_pre = 1 if sg.get("pre") else 0
         arr[i].leaky_slope = sg.get("slope", 1.0); arr[i].alpha = sg.get("alpha", 1.0)
         arr[i].addend = pa; arr[i].addend_bs = sa; arr[i].y = po; arr[i].y_bs = so
+    qo = _pitch("conv2d_multi", *qs)
     lib = _lib.load()
-    key = (B, Cin, H, W, Cout, ks, stride, dil, math)
-    nws = _ws_bytes.get(key)
-    if nws is None:
-        nws = lib.irr_conv2d_workspace_bytes(B, Cin, H, W, Cout, ks, stride, dil, math)
-        _ws_bytes[key] = nws
-    ws = torch.empty(nws // 4, dtype=torch.float32, device=x.device) if nws else None
+    ws, nws = _conv_ws(lib, x, B, Cin, H, W, Cout, ks, stride, dil, math)
     _launch("conv2d", (B, Cin, H, W, Cout, ks, stride, dil, Ho, Wo, math), lib.irr_conv2d_fwd_multi, px, sx,
             _p(packed, "packed weights", x), _p(bias, "bias", x, Cout), B, Cin, H, W, Cout, ks, stride, dil, arr, len(segs),
-            math, ws.data_ptr() if ws is not None else None, nws, _stream())
+            math, ws.data_ptr() if ws is not None else None, nws, qx, qo, _stream())
     return [sg["out"] for sg in segs]
 
 
-def resize_ac(x, OH: int, OW: int, out=None, s_even: float = 1.0, s_odd: float = 1.0):
+def resize_ac(x, OH: int, OW: int, out=None, s_even: float = 1.0, s_odd: float = 1.0, pitched: Optional[bool] = None):
     B, C, H, W = x.shape
     if out is None:
-        out = _new(x, C, OH, OW)
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _launch("resize_bilinear_ac", None, _lib.load().irr_resize_bilinear_ac_fwd, px, sx, po, so, B, C, H, W, OH, OW, s_even, s_odd, _stream())
+        out = _new(x, C, OH, OW, pitched=pitched)
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    _launch("resize_bilinear_ac", None, _lib.load().irr_resize_bilinear_ac_fwd, px, sx, po, so, B, C, H, W, OH, OW, s_even,
+            s_odd, qx, qo, _stream())
     return out
 
 
 def scale_channels(x, out=None, s_even: float = 1.0, s_odd: float = 1.0):
     B, C, H, W = x.shape
     if out is None:
-        out = _new(x, C, H, W)
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _launch("scale_channels", None, _lib.load().irr_scale_channels_fwd, px, sx, po, so, B, C, H * W, s_even, s_odd, _stream())
+        out = _new(x, C, H, W, pitched=_is_pitched(x))
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    if qx and qo and qx != qo:   # dense <-> pitched copy: the resize kernel at identical size is an exact copy with both pitches
+        return resize_ac(x, H, W, out=out, s_even=s_even, s_odd=s_odd)
+    _launch("scale_channels", None, _lib.load().irr_scale_channels_fwd, px, sx, po, so, B, C, H * (qx or qo or W), s_even, s_odd,
+            _stream())
     return out
 
 
@@ -336,9 +423,10 @@ def round_bf16(x, out=None):
     """y = x.bfloat16().float() (BASELINE config 5: bf16-valued features in the fp32 layout); ``out=x`` rounds in place."""
     B, C, H, W = x.shape
     if out is None:
-        out = _new(x, C, H, W)
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _launch("round_bf16", None, _lib.load().irr_round_bf16_fwd, px, sx, po, so, B, C, H * W, _stream())
+        out = _new(x, C, H, W, pitched=_is_pitched(x))
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    P = _pitch("round_bf16", qx, qo) or W
+    _launch("round_bf16", None, _lib.load().irr_round_bf16_fwd, px, sx, po, so, B, C, H * P, _stream())
     return out
 
 
@@ -346,26 +434,29 @@ def upsample_nearest2x(x, OH: int, OW: int, out=None):
     B, C, H, W = x.shape
     if out is None:
         out = _new(x, C, OH, OW)
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _launch("upsample_nearest2x", None, _lib.load().irr_upsample_nearest2x_fwd, px, sx, po, so, B, C, H, W, OH, OW, _stream())
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    _launch("upsample_nearest2x", None, _lib.load().irr_upsample_nearest2x_fwd, px, sx, po, so, B, C, H, W, OH, OW, qx, qo,
+            _stream())
     return out
 
 
 def sub_spatial_mean(x, out=None):
     B, C, H, W = x.shape
     if out is None:
-        out = _new(x, C, H, W)
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _launch("sub_spatial_mean", None, _lib.load().irr_sub_spatial_mean_fwd, px, sx, po, so, B, C, H, W, _stream())
+        out = _new(x, C, H, W, pitched=_is_pitched(x))
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    P = _pitch("sub_spatial_mean", qx, qo)
+    _launch("sub_spatial_mean", None, _lib.load().irr_sub_spatial_mean_fwd, px, sx, po, so, B, C, H, W, P, _stream())
     return out
 
 
 def channel_l2norm(x, out=None):
     B, C, H, W = x.shape
     if out is None:
-        out = _new(x, 1, H, W)
-    px, sx = _v(x, "x"); po, so = _v(out, "out")
-    _launch("channel_l2norm", None, _lib.load().irr_channel_l2norm_fwd, px, sx, po, so, B, C, H * W, _stream())
+        out = _new(x, 1, H, W, pitched=_is_pitched(x))
+    px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
+    P = _pitch("channel_l2norm", qx, qo) or W
+    _launch("channel_l2norm", None, _lib.load().irr_channel_l2norm_fwd, px, sx, po, so, B, C, H * P, _stream())
     return out
 
 
@@ -373,9 +464,10 @@ def refine_gather(logits, src, out=None):
     B, C, H, W = src.shape
     assert logits.shape == (B, 9, H, W)
     if out is None:
-        out = _new(src, C, H, W)
-    pl, sl = _v(logits, "logits"); ps, ss = _v(src, "src"); po, so = _v(out, "out")
-    _launch("refine_gather", None, _lib.load().irr_refine_gather_fwd, pl, sl, ps, ss, po, so, B, C, H, W, _stream())
+        out = _new(src, C, H, W, pitched=_is_pitched(src))
+    pl, sl, ql = _vp(logits, "logits"); ps, ss, qs = _vp(src, "src"); po, so, qo = _vp(out, "out")
+    P = _pitch("refine_gather", ql, qs, qo)
+    _launch("refine_gather", None, _lib.load().irr_refine_gather_fwd, pl, sl, ps, ss, po, so, B, C, H, W, P, _stream())
     return out
 
 

@@ -85,15 +85,15 @@ class PWCFamily(nn.Module):
         NB = 2 * B if self.BI else B
         df = self._div_flow
         with torch.no_grad():
-            imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()
+            imgs = ops.stack_pair(x1_raw, x2_raw)  # (2B, 3, H, W), rows pitched when W % 4 != 0
             dev = imgs.device
             pyramid = self.feature_pyramid_extractor(imgs)
             flow = occ = None
             for l, feat in enumerate(pyramid[:self.output_level + 1]):
                 _, C, h, w = feat.shape
                 if l == 0:
-                    flow_up = torch.zeros((NB, 2, h, w), dtype=torch.float32, device=dev)
-                    occ_up = torch.zeros((NB, 1, h, w), dtype=torch.float32, device=dev) if self.OCC else None
+                    flow_up = ops.empty(NB, 2, h, w, dev, zero=True)
+                    occ_up = ops.empty(NB, 1, h, w, dev, zero=True) if self.OCC else None
                 else:
                     flow_up = ops.resize_ac(flow, h, w)
                     occ_up = ops.resize_ac(occ, h, w) if self.OCC else None
@@ -102,9 +102,9 @@ class PWCFamily(nn.Module):
                     record[l] = {"flow": flow.clone()}
                     if self.OCC:
                         record[l]["occ"] = occ.clone()
-            out = {'flow': ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df)}
+            out = {'flow': ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df, pitched=False)}
             if self.OCC:
-                out['occ'] = ops.resize_ac(occ[:B], height_im, width_im)
+                out['occ'] = ops.resize_ac(occ[:B], height_im, width_im, pitched=False)
         return out
 
     def estimator_level(self, l, feat, flow_up, occ_up, height_im, width_im):
@@ -116,6 +116,7 @@ class PWCFamily(nn.Module):
                  (rows [0,B) forward, [B,2B) backward), else B
         occ_up : (NB, 1, h, w) or None (classes without the occlusion branch)
         returns (flow, occ-or-None) of this level."""
+        feat, flow_up, occ_up = ops.pitched(feat), ops.pitched(flow_up), ops.pitched(occ_up)
         B = feat.shape[0] // 2
         NB = 2 * B if self.BI else B
         C = feat.shape[1]
@@ -130,7 +131,7 @@ class PWCFamily(nn.Module):
         dev = feat.device
         df = self._div_flow
         nf = self.num_ch_in
-        buf_f = torch.empty((NB, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
+        buf_f = ops.empty(NB, 448 + nf + 2, h, w, dev)
         self._cost_volume(l, feat, B, flow_up, buf_f[:, 448:529], height_im, width_im)
         self.conv_1x1[l](x, out=buf_f[:, 529:561])
         su_l, sv_l = flow_scales(h, w, df, width_im, height_im, True)
@@ -139,7 +140,7 @@ class PWCFamily(nn.Module):
         occ = None
         if self.OCC:
             no = self.num_ch_in_occ
-            buf_o = torch.empty((NB, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
+            buf_o = ops.empty(NB, 448 + no + 1, h, w, dev)
             ops.scale_channels(buf_f[:, 448:561], out=buf_o[:, 448:561])
             ops.scale_channels(occ_up, out=buf_o[:, 561:562])
         self.flow_estimators.forward_into(buf_f, out=buf_f[:, 563:565], addend=buf_f[:, 561:563])
@@ -155,7 +156,7 @@ class PWCFamily(nn.Module):
         _, _, h, w = feat.shape
         dev = feat.device
         est = self.flow_estimators[l]
-        buf_f = torch.empty((NB, est.total_ch + (2 if last else 0), h, w), dtype=torch.float32, device=dev)
+        buf_f = ops.empty(NB, est.total_ch + (2 if last else 0), h, w, dev)
         corr = buf_f[:, 448:529]
         self._cost_volume(l, feat, B, flow_up, corr, height_im, width_im)
         if l > 0:  # cat[corr, x, flow]
@@ -164,7 +165,7 @@ class PWCFamily(nn.Module):
         occ = None
         if self.OCC:
             oest = self.occ_estimators[l]
-            buf_o = torch.empty((NB, oest.total_ch + (1 if last else 0), h, w), dtype=torch.float32, device=dev)
+            buf_o = ops.empty(NB, oest.total_ch + (1 if last else 0), h, w, dev)
             ops.scale_channels(corr, out=buf_o[:, 448:529])
             if l > 0:  # cat[corr, x1, occ] — x1 for BOTH directions (pwcnet_occ_bi.py:102-103, as written)
                 ops.scale_channels(feat[:B], out=buf_o[:B, 529:529 + C])

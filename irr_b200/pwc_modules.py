@@ -20,6 +20,7 @@ def set_conv_math(math: int) -> None:
     fall back to the CUDA-core kernel *inside the native library's dispatch table*, never to PyTorch."""
     global _default_math
     _default_math = math
+    ops.set_pitch_enabled(math == ops.MATH_TC_3XF16)   # only the 3xF16 conv path reads / writes row-pitched tensors
 
 
 def get_conv_math() -> int:
@@ -118,7 +119,7 @@ def upsample2d_as(inputs, target_as, mode="bilinear"):
     """models/pwc_modules.py:65-67."""
     assert mode == "bilinear"
     _, _, h, w = target_as.size()
-    return ops.resize_ac(inputs, h, w)
+    return ops.resize_ac(inputs, h, w, pitched=False)   # the reference-API function returns dense rows
 
 
 def flow_scales(h, w, div_flow, width_im, height_im, to_local=True):
@@ -259,9 +260,9 @@ class _DenseEstimator(nn.Module):
         co = self.ch_out
         dev = buf.device
         if out is None:
-            out = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
-        p5 = torch.empty((B, 32, H, W), dtype=torch.float32, device=dev)
-        pl = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
+            out = ops.new_like(buf, co)
+        p5 = ops.new_like(buf, 32)
+        pl = ops.new_like(buf, co)
         ops.conv2d_multi(buf[:, 96:self.total_ch], pB, bB, 96 + co, 3, [
             dict(n_begin=0, out=buf[:, 32:96], slope=0.1),
             dict(n_begin=64, out=p5, slope=1.0),
@@ -295,7 +296,7 @@ class _DenseEstimator(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        buf = torch.empty((B, self.total_ch, H, W), dtype=torch.float32, device=x.device)
+        buf = ops.empty(B, self.total_ch, H, W, x.device)
         ops.scale_channels(x, out=buf[:, 448:])
         x_out = self.forward_into(buf)
         return buf, x_out

@@ -43,13 +43,14 @@ class PWCNet(nn.Module):
         feat   : (2B, C_l, h, w) rows [0,B) = x1 features, rows [B,2B) = x2 features
         flow_up: (B, 2, h, w) the previous level's flow already resized to this level (ignored at l == 0)
         returns this level's flow (B, 2, h, w) — after the context network at the output level."""
+        feat, flow_up = ops.pitched(feat), ops.pitched(flow_up)
         B = feat.shape[0] // 2
         df = self._div_flow
         x1, x2 = feat[:B], feat[B:]
         _, C, h, w = x1.shape
         est = self.flow_estimators[l]
         last = l == self.output_level
-        buf = torch.empty((B, est.total_ch + (2 if last else 0), h, w), dtype=torch.float32, device=feat.device)
+        buf = ops.empty(B, est.total_ch + (2 if last else 0), h, w, feat.device)
         corr = buf[:, 448:529]
         if l == 0:  # pwcnet.py:66-68,73-74
             ops.correlation(x1, x2, out=corr, slope=0.1)
@@ -78,7 +79,7 @@ class PWCNet(nn.Module):
         B, _, height_im, width_im = x1_raw.shape
         df = self._div_flow
         with torch.no_grad():
-            imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()
+            imgs = ops.stack_pair(x1_raw, x2_raw)  # (2B, 3, H, W), rows pitched when W % 4 != 0
             pyramid = self.feature_pyramid_extractor(imgs)
             flow = None
             for l, feat in enumerate(pyramid[:self.output_level + 1]):
@@ -89,5 +90,5 @@ class PWCNet(nn.Module):
                 if record is not None:
                     rec_l = record[l] = {}
                 flow = self.estimator_level(l, feat, flow, height_im, width_im, rec_l)
-            out = ops.resize_ac(flow, height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df)  # pwcnet.py:97
+            out = ops.resize_ac(flow, height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df, pitched=False)  # pwcnet.py:97
         return {'flow': out}

@@ -48,13 +48,14 @@ class PWCNet(nn.Module):
         flow_up: (2B, 2, h, w) flow in GLOBAL units already resized to this level (zeros at l == 0); rows [0,B) forward
         occ_up : (2B, 1, h, w)
         returns (flow in GLOBAL units, occ) of this level on the 2B batch."""
+        feat, flow_up, occ_up = ops.pitched(feat), ops.pitched(flow_up), ops.pitched(occ_up)
         B2, C, h, w = feat.shape
         B = B2 // 2
         dev = feat.device
         df = self._div_flow
         nf, no = self.num_ch_in_flo, self.num_ch_in_occ
-        buf_f = torch.empty((B2, 448 + nf + 2, h, w), dtype=torch.float32, device=dev)
-        buf_o = torch.empty((B2, 448 + no + 1, h, w), dtype=torch.float32, device=dev)
+        buf_f = ops.empty(B2, 448 + nf + 2, h, w, dev)
+        buf_o = ops.empty(B2, 448 + no + 1, h, w, dev)
         corr = buf_f[:, 448:529]
         if l == 0:  # pwcnet_irr_occ_bi.py:68-70,82-85
             ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
@@ -86,15 +87,15 @@ class PWCNet(nn.Module):
         B2 = 2 * B
         df = self._div_flow
         with torch.no_grad():
-            imgs = torch.cat([x1_raw, x2_raw], dim=0).float().contiguous()
+            imgs = ops.stack_pair(x1_raw, x2_raw)  # (2B, 3, H, W), rows pitched when W % 4 != 0
             dev = imgs.device
             pyramid = self.feature_pyramid_extractor(imgs)
             flow = occ = None
             for l, feat in enumerate(pyramid[:self.output_level + 1]):
                 _, C, h, w = feat.shape
                 if l == 0:
-                    flow_up = torch.zeros((B2, 2, h, w), dtype=torch.float32, device=dev)
-                    occ_up = torch.zeros((B2, 1, h, w), dtype=torch.float32, device=dev)
+                    flow_up = ops.empty(B2, 2, h, w, dev, zero=True)
+                    occ_up = ops.empty(B2, 1, h, w, dev, zero=True)
                 else:
                     flow_up = ops.resize_ac(flow, h, w)
                     occ_up = ops.resize_ac(occ, h, w)
@@ -102,6 +103,6 @@ class PWCNet(nn.Module):
                 if record is not None:
                     rec_l = record[l] = {}
                 flow, occ = self.estimator_level(l, feat, flow_up, occ_up, height_im, width_im, rec_l)
-            out_flow = ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df)  # :130
-            out_occ = ops.resize_ac(occ[:B], height_im, width_im)  # :131
+            out_flow = ops.resize_ac(flow[:B], height_im, width_im, s_even=1.0 / df, s_odd=1.0 / df, pitched=False)  # :130
+            out_occ = ops.resize_ac(occ[:B], height_im, width_im, pitched=False)  # :131
         return {'flow': out_flow, 'occ': out_occ}

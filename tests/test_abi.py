@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(fns) >= 18
     for name in fns:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.irr_abi_version() == 1
+    assert lib.irr_abi_version() == 2
 
 
 def test_ctypes_table_matches_header():
