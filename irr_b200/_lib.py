@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libirr_b200.so")
+# IRR_B200_LIB: load an experimental build of the same sources instead (kernel A/B runs only)
+LIB_PATH = os.environ.get("IRR_B200_LIB") or os.path.join(_HERE, "libirr_b200.so")
 
 c_fp = C.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
 

@@ -126,7 +126,7 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
   const int nchunks = (C + CC - 1) / CC;
   const int ksplit = SPLIT ? sp.ksplit : 1;
   const int nvt = ntiles * ksplit;
-  const bool con = (ctr & 1) && blockIdx.x == 0 && tid == 0;
+  const bool con = ctr && blockIdx.x == 0 && tid == 0;
   const long long ct0 = con ? clock64() : 0;
   // Thread -> (tile row r, displacement row dyi, 8-pixel strip s8).  The 72 (r, dyi) pairs are dealt to the 9 warps
   // sorted by the f2 halo row they read (h = r + dyi), 8 pairs x 4 strips per warp: a warp then touches only 2-4
@@ -135,16 +135,13 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
   // 6 LDS.128 per channel cost 24 wavefronts per warp against 18 issue slots of FFMA: shared memory, not the FMA
   // pipe, was the limiter.  Sorted, the same loads cost ~12 wavefronts.
   const int lane = tid & 31;
-  // ctr bit 1 (IRR_CORR_LMAP=1, experiment): lane = strip * 8 + pair, so that a QUARTER warp is one strip of 8 pairs whose
-  // f2 rows coincide (1-2 distinct 16-byte chunks per quarter) instead of 2 pairs x 4 strips
-  const bool lmap = (ctr & 2) != 0;
-  const int s8 = lmap ? (lane >> 3) : (lane & 3);
+  const int s8 = lane & 3;
   int r, dyi;
   bool pair_ok;
   {
     // p-th pair in (h, r) order; halo row h holds min(h, TH-1, ND-1, TH+ND-2-h) + 1 pairs.  A 7-row tile has 63 pairs:
     // the last four lanes of warp 7 shadow pair 0 (their loads stay in bounds, they store nothing).
-    int p = (tid >> 5) * 8 + (lmap ? (lane & 7) : (lane >> 2)), h = 0;
+    int p = (tid >> 5) * 8 + (lane >> 2), h = 0;
     pair_ok = p < NPAIR;
     if (!pair_ok) p = 0;
     for (;;) {
@@ -827,7 +824,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
   } else if (!(FUSED && PRETAB) && tid == (FUSED ? T_ISSUER_FUSED : NCOMP)) {
     // ============================== COPY ISSUER (one thread) ==============================
     int gchunk = 0, it = 0;
-    const bool con = (ctr & 1) && blockIdx.x == 0;
+    const bool con = ctr && blockIdx.x == 0;
     const long long ct0 = con ? clock64() : 0;
     for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
       const int tile = SPLIT ? vt / ksplit : vt, ks = SPLIT ? vt - tile * ksplit : 0;
@@ -872,7 +869,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     const int pt = tid - NCOMP - ((tid >> 5) > (T_ISSUER_FUSED >> 5) ? 32 : 0);
     const int lane = tid & 31;
     int gchunk = 0, it = 0;
-    const bool con = (ctr & 1) && blockIdx.x == 0 && pt == 0;
+    const bool con = ctr && blockIdx.x == 0 && pt == 0;
     const long long ct0 = con ? clock64() : 0;
     // PRETAB: this thread's raw table entries of the NEXT tile (loaded while the current tile is sampled)
     int pre_e[T_KPOS];
@@ -1137,9 +1134,8 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
     CUtensorMap m1, m2;
     if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC, P) &&
         make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC, P)) {
-      static const bool lmap_env = [] { const char* e = getenv("IRR_CORR_LMAP"); return e && e[0] == '1'; }();
-      const int ctr = (corr_ctr_on() ? 1 : 0) | (lmap_env ? 2 : 0);
-      if (ctr & 1) {
+      const int ctr = corr_ctr_on() ? 1 : 0;
+      if (ctr) {
         static const unsigned long long zeros[32] = {0};
         cudaMemcpyToSymbolAsync(corr_ctr, zeros, sizeof(zeros), 0, cudaMemcpyHostToDevice, st);
       }
@@ -1149,7 +1145,7 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
       float4* tabW = nullptr;
       int* tabI = nullptr;
       // tap table from a pre-pass (fused launches): the table goes first in the workspace
-      if (FUSED && wsp != nullptr && (reinterpret_cast<uintptr_t>(wsp) & 255) == 0 && !corr_no_pretab() && !(ctr & 1) && H < 32768 &&
+      if (FUSED && wsp != nullptr && (reinterpret_cast<uintptr_t>(wsp) & 255) == 0 && !corr_no_pretab() && !ctr && H < 32768 &&
           W < 16384 && corr_tab_bytes(B, H, W) <= ws_left) {
         const size_t n = (size_t)B * H * W;
         tabW = reinterpret_cast<float4*>(wsp);
