@@ -100,6 +100,21 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
                                 int f2_batch_shift, float leaky_slope, int grid_flags, void* workspace,
                                 size_t workspace_bytes, int pitch, irr_stream_t stream);
 
+/* The same with a choice of INPUT STORAGE for f1 / f2 (SURVEY.md §8(b) sketch `dtype_in`; BASELINE configs[4] "mixed bf16
+ * features"): dtype_in = IRR_DTYPE_BF16 reads packed bf16 (2 bytes per element: half the f1 / f2 bytes of the launch);
+ * f1_bs / f2_bs / in_pitch are then in bf16 ELEMENTS and must be multiples of 8 with 16-byte aligned bases (TMA rows of
+ * whole 16-byte units; IRR_E_ALIGN otherwise — there is no unaligned bf16 path).  flow / out stay fp32 with row pitch
+ * `pitch`.  The arithmetic is the fp32 kernel's on the converted values: results are bit-identical to
+ * irr_warp_correlation_fwd_ws on the same values held in fp32.  The reference has no such mode
+ * (correlation_cuda_kernel.cu:352 dispatches float / double / half as the tensor comes). */
+#define IRR_DTYPE_F32 0
+#define IRR_DTYPE_BF16 1
+int irr_warp_correlation_fwd_dt(const void* f1, long long f1_bs, const void* f2, long long f2_bs, int dtype_in, int in_pitch,
+                                const float* flow, long long flow_bs, const float* lin_x, const float* lin_y, float* out,
+                                long long out_bs, int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
+                                int f2_batch_shift, float leaky_slope, int grid_flags, void* workspace,
+                                size_t workspace_bytes, int pitch, irr_stream_t stream);
+
 /* A2 standalone — out[b] = mask*warp(x[(b+x_batch_shift) mod B], flow[b]);  if minuend != NULL:
  * out = minuend - mask*warp(...)   (IRR_PWC.py:132-133,144-145 feed `a - warp(b)` to the refinement nets).
  * mask_out (optional, B x H x W floats 0/1) receives the validity mask. */
@@ -195,6 +210,12 @@ int irr_scale_channels_fwd(const float* x, long long x_bs, float* y, long long y
  * y = float(bfloat16(x)), round-to-nearest-even, on a channel-slice view.  In place (y == x) is allowed. */
 int irr_round_bf16_fwd(const float* x, long long x_bs, float* y, long long y_bs, int B, int C, long long HW,
                        irr_stream_t stream);
+
+/* The same rounding with a second, PACKED destination: y16[b,c,h,w] = bf16_rn(x[b,c,h,w]) as 2-byte elements (batch stride
+ * y16_bs and row pitch y16_pitch in bf16 elements) for irr_warp_correlation_fwd_dt; y (fp32 layout, pitch x_pitch, may be x
+ * itself or NULL) receives float(bf16_rn(x)) as irr_round_bf16_fwd does. */
+int irr_round_bf16_store_fwd(const float* x, long long x_bs, int x_pitch, float* y, long long y_bs, void* y16,
+                             long long y16_bs, int y16_pitch, int B, int C, int H, int W, irr_stream_t stream);
 
 /* A10 — upsample_factor2 (models/irr_modules.py:21-27): nearest x2, then (only if (OH,OW) != (2H,2W)) bilinear
  * align_corners=False resize to OH x OW. */

@@ -84,6 +84,7 @@ class PWCNet(nn.Module):
         # BASELINE config 5 ("mixed bf16 features"): "bf16" rounds the feature pyramid to bf16 values before the warp /
         # correlation / 1x1 convs (a capability the fp32-only reference does not have; default = the reference's fp32)
         self.feature_dtype = "fp32"
+        self.bf16_storage = True   # with feature_dtype "bf16": the cost volumes read a packed bf16 copy of the features
         # Dead-branch elimination for the eval forward (off by default = the reference's executed work, layer for
         # layer).  In eval mode the reference returns only flow_f and occ_f (IRR_PWC.py:176-184); nothing that feeds
         # them reads the BACKWARD occlusion chain: occ_b enters only its own estimator / context / refinement /
@@ -100,13 +101,15 @@ class PWCNet(nn.Module):
         return self
 
     # ------------------------------------------------------------------------------------------------ stages
-    def estimator_level(self, l, feat, flow_up, occ_up, imgs, height_im, width_im, record=None):
+    def estimator_level(self, l, feat, flow_up, occ_up, imgs, height_im, width_im, record=None, feat16=None):
         """One pass of IRR_PWC.py:75-147 for pyramid level l <= 4 on the 2B batch.
 
         feat   : (2B, C_l, h, w)  rows [0,B) = x1 features, rows [B,2B) = x2 features
         flow_up: (2B, 2, h, w) flow in GLOBAL units already resized to this level (zeros at l == 0); rows [0,B) forward
         occ_up : (2B, 1, h, w)
         imgs   : (2B, 3, H, W)
+        feat16 : optional packed bf16 copy of ``feat`` (feature_dtype "bf16"): the cost volume reads it instead — half the
+                 f1 / f2 bytes, bit-identical results (ops.round_bf16_store)
         returns (flow, occ) for this level (flow in GLOBAL units), each on the 2B batch."""
         feat, flow_up, occ_up, imgs = ops.pitched(feat), ops.pitched(flow_up), ops.pitched(occ_up), ops.pitched(imgs)
         B2, C, h, w = feat.shape
@@ -121,10 +124,11 @@ class PWCNet(nn.Module):
         BO = B if self.eval_prune_dead else B2   # rows the occlusion branch runs on
         buf_o = ops.empty(BO, 448 + no + 1, h, w, dev)
         corr = buf_f[:, 448:529]
+        cf = feat if feat16 is None else feat16
         if l == 0:  # IRR_PWC.py:78-80,90-95 — no warp at the coarsest level
-            ops.correlation(feat, feat, out=corr, shift=B, slope=0.1)
+            ops.correlation(cf, cf, out=corr, shift=B, slope=0.1)
         else:       # :86-95 fused
-            ops.warp_correlation(feat, feat, flow_up, height_im, width_im, df, out=corr, shift=B, slope=0.1)
+            ops.warp_correlation(cf, cf, flow_up, height_im, width_im, df, out=corr, shift=B, slope=0.1)
         x1by1 = buf_f[:, 529:561]
         if l != self.output_level:  # :97-102
             self.conv_1x1[l](feat, out=x1by1)
@@ -239,9 +243,15 @@ class PWCNet(nn.Module):
         with torch.no_grad():
             imgs = ops.stack_pair(x1_raw, x2_raw)  # (2B, 3, H, W), rows pitched when W % 4 != 0
             pyramid = self.feature_pyramid_extractor(imgs)
+            pyr16 = [None] * (len(pyramid) + 1)
             if self.feature_dtype == "bf16":
-                for f in pyramid:
-                    ops.round_bf16(f, out=f)
+                # bf16 VALUES in the fp32 layout for the convs / warps; for the levels that feed a cost volume also a packed
+                # bf16 copy (STORAGE), written in the same pass, which the correlation kernels read
+                for l, f in enumerate(pyramid):
+                    if l <= self.output_level and self.bf16_storage:
+                        pyr16[l] = ops.round_bf16_store(f, round_in_place=True)
+                    else:
+                        ops.round_bf16(f, out=f)
             pyramid = pyramid + [imgs]
             flow = occ = None
             for l, feat in enumerate(pyramid):
@@ -259,7 +269,7 @@ class PWCNet(nn.Module):
                         occ_up = ops.resize_ac(occ, h, w)
                     if rec_l is not None:
                         rec_l["feat"] = feat.clone(); rec_l["flow_up"] = flow_up.clone(); rec_l["occ_up"] = occ_up.clone()
-                    flow, occ = self.estimator_level(l, feat, flow_up, occ_up, imgs, height_im, width_im, rec_l)
+                    flow, occ = self.estimator_level(l, feat, flow_up, occ_up, imgs, height_im, width_im, rec_l, pyr16[l])
                 else:
                     flow = ops.resize_ac(flow, h, w)
                     if rec_l is not None:

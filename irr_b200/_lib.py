@@ -37,6 +37,9 @@ PROTOTYPES = {
     "irr_correlation_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
     "irr_warp_correlation_fwd_ws": [c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i,
                                     c_i, c_f, c_i, c_i, c_f, c_i, c_fp, C.c_size_t, c_i, c_fp],
+    "irr_warp_correlation_fwd_dt": [c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_i, c_i, c_i, c_i,
+                                    c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_fp, C.c_size_t, c_i, c_fp],
+    "irr_round_bf16_store_fwd": [c_fp, c_ll, c_i, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_fp],
     "irr_warp_fwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_i, c_i, c_i, c_i, c_i, c_i,
                      c_f, c_i, c_i, c_i, c_fp],
     "irr_warp_bwd": [c_fp, c_ll, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f,

@@ -62,18 +62,21 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-bool make_nchw_map(CUtensorMap* map, const float* base, long long bs, int B, int C, int H, int W, int bw, int bh,
-                   int bc, int pitch) {
+bool make_nchw_map(CUtensorMap* map, const void* base, long long bs, int B, int C, int H, int W, int bw, int bh,
+                   int bc, int pitch, int elem_bytes) {
   EncodeTiledFn enc = encode_tiled();
   const int P = pitch > 0 ? pitch : W;   // row pitch in elements; the map's inner dimension stays W: columns >= W read 0
-  if (!enc || (P % 4) != 0 || P < W || (bs % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
-  if (bw > 256 || bh > 256 || bc > 256 || ((bw * 4) % 16) != 0) return false;
+  const int E = elem_bytes, A = 16 / E;  // elements per 16 bytes
+  if (E != 4 && E != 2) return false;
+  if (!enc || (P % A) != 0 || P < W || (bs % A) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  if (bw > 256 || bh > 256 || bc > 256 || ((bw * E) % 16) != 0) return false;
   memset(map, 0, sizeof(*map));
   cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)P * 4, (cuuint64_t)H * P * 4, (cuuint64_t)bs * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)P * E, (cuuint64_t)H * P * E, (cuuint64_t)bs * E};
   cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+  return enc(map, E == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+             strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -48,8 +48,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_tiled();
 // fp32 NCHW channel-slice view (W, H, C, B; batch stride bs elements) -> tiled tensor map with the given box
 // (elements, innermost first).  Out-of-bounds box elements read as zero.  Needs W % 4 == 0, bs % 4 == 0, 16-byte base.
-bool make_nchw_map(CUtensorMap* map, const float* base, long long bs, int B, int C, int H, int W, int bw, int bh, int bc,
-                   int pitch = 0);
+// elem_bytes = 2: the same view over bf16 storage (strides / pitch in bf16 elements; needs pitch % 8 == 0, bs % 8 == 0).
+bool make_nchw_map(CUtensorMap* map, const void* base, long long bs, int B, int C, int H, int W, int bw, int bh, int bc,
+                   int pitch = 0, int elem_bytes = 4);
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 

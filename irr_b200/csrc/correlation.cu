@@ -66,6 +66,23 @@ constexpr int NHALO = F2_H * F2_WV;         // 640
 constexpr int NF1 = TH * TW;                // 256
 constexpr int FP_H = IRR_CORR_FP_H, FP_W = 48; // fused variant: source footprint window per channel (texels)
 constexpr int FP_ELEMS = CC * FP_H * FP_W;     // 9216 floats per ring slot
+// bf16 INPUT STORAGE (dtype_in = 1, TMA kernels only): the ring slots keep their fp32-sized regions and byte offsets, the
+// bf16 tiles use the front of them.  Row pitches in bf16 elements are multiples of 8 (TMA box rows of whole 16-byte units):
+// f1 [8][TH][40]; plain f2 [8][16][48] with the box origin at x0 - 8 (a 16-byte aligned inner coordinate), i.e. halo column
+// hx sits at tile column hx + 4; fused: the footprint [8][FP_H][48] is bf16, the warped halo tile the samplers write stays fp32.
+constexpr int F1_P16 = 40, F2_P16 = 48, F2_SKIP16 = 4;
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+template <bool BF>
+__device__ __forceinline__ float ld_in(const void* base, long long i) {   // element i of an fp32 / bf16 array
+  if (BF) return __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(base)[i] << 16);
+  return reinterpret_cast<const float*>(base)[i];
+}
+template <bool BF>
+__device__ __forceinline__ float ldg_in(const void* base, long long i) {
+  if (BF) return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(base) + i) << 16);
+  return __ldg(reinterpret_cast<const float*>(base) + i);
+}
 constexpr int CORR_SMEM_PLAIN = CORR_STAGES * STAGE_ELEMS * 4 + 64;
 constexpr int CORR_SMEM_FUSED = CORR_SMEM_PLAIN + CORR_STAGES * FP_ELEMS * 4;
 
@@ -114,7 +131,7 @@ struct CSplit {
   float* ws; long long ws_stride;   // [ksplit][B][81][H][W]
 };
 
-template <int NS, bool PREFETCH, class Hook, bool SPLIT = false>
+template <int NS, bool PREFETCH, class Hook, bool SPLIT = false, bool BF1 = false, bool BF2 = false>
 __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem, uint32_t full0, uint32_t empty0,
                                              const float* __restrict__ f1, long long f1_bs,
                                              const float* __restrict__ f2, long long f2_bs, float* __restrict__ out,
@@ -208,15 +225,32 @@ __device__ __forceinline__ void corr_compute(const Hook& hook, const float* smem
       const float* f2s = f1s + F1_ELEMS;
 #pragma unroll 2
       for (int cc = 0; cc < CC; ++cc) {
-        const float4* ap = reinterpret_cast<const float4*>(f1s + (cc * TH + r) * F1_P + s8 * PX);
-        const float4* bp = reinterpret_cast<const float4*>(f2s + (cc * F2_H + r + dyi) * F2_P + s8 * PX);
         float a[PX], bv[PX + 2 * MD];
-        float4 t0 = ap[0], t1 = ap[1];
-        a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+        if (BF1) {   // 8 bf16 pixels = one 16-byte load; bf16 -> fp32 is a shift / a mask
+          const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(f1s) + (cc * TH + r) * F1_P16 +
+                                                          s8 * PX);
+          a[0] = bf_lo(t.x); a[1] = bf_hi(t.x); a[2] = bf_lo(t.y); a[3] = bf_hi(t.y);
+          a[4] = bf_lo(t.z); a[5] = bf_hi(t.z); a[6] = bf_lo(t.w); a[7] = bf_hi(t.w);
+        } else {
+          const float4* ap = reinterpret_cast<const float4*>(f1s + (cc * TH + r) * F1_P + s8 * PX);
+          float4 t0 = ap[0], t1 = ap[1];
+          a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+        }
+        if (BF2) {   // 16 bf16 halo pixels starting 8 bytes into a 16-byte unit: four 8-byte loads
+          const uint2* bp = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(f2s) +
+                                                           (cc * F2_H + r + dyi) * F2_P16 + F2_SKIP16 + s8 * PX);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 t = bp[q];
-          bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+          for (int q = 0; q < 4; ++q) {
+            const uint2 t = bp[q];
+            bv[4 * q] = bf_lo(t.x); bv[4 * q + 1] = bf_hi(t.x); bv[4 * q + 2] = bf_lo(t.y); bv[4 * q + 3] = bf_hi(t.y);
+          }
+        } else {
+          const float4* bp = reinterpret_cast<const float4*>(f2s + (cc * F2_H + r + dyi) * F2_P + s8 * PX);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 t = bp[q];
+            bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+          }
         }
 #pragma unroll
         for (int d = 0; d < ND; ++d)
@@ -561,6 +595,7 @@ struct TapSetup {
   const float* flow; long long flow_bs;
   GridArgs g;
   int H, W, P, tiles_x, tiles_y;
+  int Pi, xalign;  // row pitch of f2 (elements of ITS dtype); the footprint origin is aligned down to xalign + 1 elements (16 bytes)
   float* tab;      // [2][T_TAB_WORDS]
   int* meta;       // [2][4] {oy, ox, foot, -}
   int* red;        // [3][4] {ymin, ymax, xmin, xmax}
@@ -625,7 +660,7 @@ struct TapSetup {
     const int ymin = rd[0], ymax = rd[1], xmin = rd[2], xmax = rd[3];
     const bool any_live = ymax >= ymin;
     // TMA traps on an inner coordinate that is not 16-byte aligned (measured): align the window origin down
-    const int oy = any_live ? ymin : 0, ox = any_live ? (xmin & ~3) : 0;
+    const int oy = any_live ? ymin : 0, ox = any_live ? (xmin & ~xalign) : 0;
     const int foot = (!any_live || ((ymax - oy) < FP_H && (xmax - ox) < FP_W)) ? 1 : 0;
     float4* tw = reinterpret_cast<float4*>(tab + slot * T_TAB_WORDS);
     int* to = reinterpret_cast<int*>(tab + slot * T_TAB_WORDS + NHALO * 4);
@@ -634,7 +669,7 @@ struct TapSetup {
       const int h = tid + k * NCOMP;
       if (h < NHALO) {
         tw[h] = wq[k];
-        const int off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * P + xa_[k];
+        const int off = foot ? (ya_[k] - oy) * FP_W + (xa_[k] - ox) : ya_[k] * Pi + xa_[k];
         to[h] = dxy[k] < 0 ? -1 : ((off << 2) | dxy[k]);
       }
     }
@@ -676,14 +711,20 @@ __global__ void __launch_bounds__(256) corr_taps_kernel(const float* __restrict_
   tabI[(size_t)b * HW + pix] = e;
 }
 
-template <bool FUSED, bool SPLIT, bool PRETAB>
+// BF: f1 / f2 are bf16 storage (their batch strides and the pitch Pi in bf16 elements); flow / out stay fp32 with pitch P.
+template <bool FUSED, bool SPLIT, bool PRETAB, bool BF = false>
 __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
     corr_tma_kernel(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                     const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2, long long f2_bs,
                     const float* __restrict__ flow, long long flow_bs, float* __restrict__ out, long long out_bs,
-                    GridArgs g, int B, int C, int H, int W, int P, int shift, float slope, int vec_ok, int tiles_x,
+                    GridArgs g, int B, int C, int H, int W, int P, int Pi, int shift, float slope, int vec_ok, int tiles_x,
                     int tiles_y, int ntiles, int ctr, CSplit sp, const float4* __restrict__ tabW,
                     const int* __restrict__ tabI) {
+  static_assert(!(BF && PRETAB), "the pre-pass variant is fp32 only");
+  constexpr uint32_t F1_BYTES = BF ? CC * TH * F1_P16 * 2 : T_F1_BYTES;
+  constexpr uint32_t F2_BYTES = BF ? CC * F2_H * F2_P16 * 2 : T_F2_BYTES;
+  constexpr uint32_t FP_BYTES = BF ? T_FP_BYTES / 2 : T_FP_BYTES;
+  constexpr int XORG = BF ? 2 * MD : MD;   // plain f2 box origin x0 - XORG: a 16-byte aligned inner coordinate
   constexpr int NS = FUSED ? T_NS_FUSED : T_NS_PLAIN;
   const int ksplit = SPLIT ? sp.ksplit : 1;
   const int nvt = ntiles * ksplit;
@@ -702,7 +743,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
   int* red = meta + 8;
 
   const int tid = threadIdx.x;
-  const int HW = H * P;    // channel stride (pitched rows)
+  const int HWi = H * Pi;  // channel stride of f1 / f2 (their own pitch and element type)
   const int HWd = H * W;   // dense: the pre-pass' tap table
   const int nchunks = (C + CC - 1) / CC;
   if (tid == 0) {
@@ -728,11 +769,13 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       TapSetup hook;
       hook.flow = flow; hook.flow_bs = flow_bs; hook.g = g; hook.H = H; hook.W = W; hook.P = P; hook.tiles_x = tiles_x;
       hook.tiles_y = tiles_y; hook.tab = tab; hook.meta = meta; hook.red = red; hook.tabfull0 = tabfull(0);
-      corr_compute<NS, false, TapSetup, SPLIT>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C, H, W,
-                                               P, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
+      hook.Pi = Pi; hook.xalign = BF ? 7 : 3;
+      corr_compute<NS, false, TapSetup, SPLIT, BF, false>(hook, smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B, C,
+                                                          H, W, P, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
     } else {
-      corr_compute<NS, false, NoTileHook, SPLIT>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs, out, out_bs, B,
-                                                 C, H, W, P, shift, slope, vec_ok, tiles_x, tiles_y, ntiles, ctr, sp);
+      corr_compute<NS, false, NoTileHook, SPLIT, BF, BF && !FUSED>(NoTileHook(), smem, full(0), empty(0), f1, f1_bs, f2, f2_bs,
+                                                                   out, out_bs, B, C, H, W, P, shift, slope, vec_ok, tiles_x,
+                                                                   tiles_y, ntiles, ctr, sp);
     }
   } else if (FUSED && PRETAB && (tid >> 5) == (T_ISSUER_FUSED >> 5)) {
     // ============================== COPY ISSUER, table from the pre-pass (one warp) ==============================
@@ -846,16 +889,16 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         mbar_wait_ctr(empty(s), (uint32_t)(((gchunk / NS) & 1) ^ 1), con, 9);
         const uint32_t st = smem_u32(smem + s * STAGE_ELEMS);
         if (!FUSED) {
-          mbar_expect_tx(full(s), T_F1_BYTES + T_F2_BYTES);
+          mbar_expect_tx(full(s), F1_BYTES + F2_BYTES);
           tma_load_4d(st, &m1, x0, y0, ci * CC, b, full(s));
-          tma_load_4d(st + T_F1_BYTES, &m2, x0 - MD, y0 - MD, ci * CC, b2, full(s));
+          tma_load_4d(st + T_F1_BYTES, &m2, x0 - XORG, y0 - MD, ci * CC, b2, full(s));   // the f2 REGION keeps its fp32 offset
         } else {
-          mbar_expect_tx(full(s), T_F1_BYTES);
+          mbar_expect_tx(full(s), F1_BYTES);
           tma_load_4d(st, &m1, x0, y0, ci * CC, b, full(s));
           const int fs = gchunk % T_NFS;
           mbar_wait_ctr(fpempty(fs), (uint32_t)(((gchunk / T_NFS) & 1) ^ 1), con, 10);
           if (foot) {
-            mbar_expect_tx(fpfull(fs), T_FP_BYTES);
+            mbar_expect_tx(fpfull(fs), FP_BYTES);
             tma_load_4d(smem_u32(fpr + fs * FP_ELEMS), &m2, ox, oy, ci * CC, b2, fpfull(fs));
           } else {
             mbar_arrive(fpfull(fs));  // divergent tile: the samplers gather from global memory, keep the phases moving
@@ -899,7 +942,9 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
       const int b = tile / (tiles_x * tiles_y);
       int b2 = b + shift;
       if (b2 >= B) b2 -= B;
-      const float* f2b = f2 + (size_t)b2 * f2_bs;
+      // f2 of this tile's image (element offsets in f2's own type)
+      const void* f2b = BF ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(f2) + (size_t)b2 * f2_bs)
+                           : static_cast<const void*>(f2 + (size_t)b2 * f2_bs);
       // this tile's taps, from the table the compute warps filled one tile ago (PRETAB: from the pre-pass' table)
       const int slot = it & 1;
       mbar_wait_ctr(tabfull(slot), (uint32_t)((it >> 1) & 1), con, 16);
@@ -916,7 +961,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
           od[k] = -1;
           if (pre_e[k] >= 0) {
             const int ya = pre_e[k] >> 16, xa = (pre_e[k] >> 2) & 0x3fff;
-            const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * P + xa;
+            const int off = foot ? (ya - oy) * FP_W + (xa - ox) : ya * Pi + xa;
             od[k] = (off << 2) | (pre_e[k] & 3);
             wq[k] = pre_w[k];
           }
@@ -939,7 +984,7 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
         float* st = smem + s * STAGE_ELEMS + F1_ELEMS;
         const int c0 = ci * CC;
         if (foot) {
-          const float* fp = fpr + fs * FP_ELEMS;
+          const void* fp = fpr + fs * FP_ELEMS;   // bf16 footprints use the first half of the slot
 #pragma unroll
           for (int k = 0; k < T_KPOS; ++k) {
             const int h = pt + k * T_NSAMP;
@@ -947,15 +992,16 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
               const int hr = h / F2_WV, hx = h - hr * F2_WV;
               float* dst = st + hr * F2_P + hx;
               const bool live = od[k] >= 0;
-              const float* pq = fp + (live ? (od[k] >> 2) : 0);
+              const int pq = live ? (od[k] >> 2) : 0;
               const int dx = od[k] & 1, dy = (od[k] & 2) ? FP_W : 0;  // dead: od = -1 -> dx = 1, dy = FP_W, still inside
               // all 32 tap loads of the position first, then the arithmetic, then the stores: a shared-memory store between
               // the channels would serialise them (the compiler cannot prove dst and the footprint do not alias)
               float t[4][CC];
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
-                const float* pc = pq + cc * (FP_H * FP_W);
-                t[0][cc] = pc[0]; t[1][cc] = pc[dx]; t[2][cc] = pc[dy]; t[3][cc] = pc[dy + dx];
+                const int pc = pq + cc * (FP_H * FP_W);
+                t[0][cc] = ld_in<BF>(fp, pc); t[1][cc] = ld_in<BF>(fp, pc + dx);
+                t[2][cc] = ld_in<BF>(fp, pc + dy); t[3][cc] = ld_in<BF>(fp, pc + dy + dx);
               }
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
@@ -977,17 +1023,17 @@ __global__ void __launch_bounds__(FUSED ? CORR_THREADS : T_PLAIN_THREADS, 1)
               const int hr = h / F2_WV, hx = h - hr * F2_WV;
               float* dst = st + hr * F2_P + hx;
               const bool live = od[k] >= 0;
-              const float* pq = f2b + (size_t)c0 * HW + (live ? (od[k] >> 2) : 0);
-              const int dx = live ? (od[k] & 1) : 0, dy = (live && (od[k] & 2)) ? P : 0;
+              const long long pq = (long long)c0 * HWi + (live ? (od[k] >> 2) : 0);
+              const int dx = live ? (od[k] & 1) : 0, dy = (live && (od[k] & 2)) ? Pi : 0;
               float t[4][CC];
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
                 const bool okc = live && (c0 + cc < C);
-                const float* pc = pq + (size_t)cc * HW;
-                t[0][cc] = okc ? __ldg(pc) : 0.f;
-                t[1][cc] = okc ? __ldg(pc + dx) : 0.f;
-                t[2][cc] = okc ? __ldg(pc + dy) : 0.f;
-                t[3][cc] = okc ? __ldg(pc + dy + dx) : 0.f;
+                const long long pc = pq + (long long)cc * HWi;
+                t[0][cc] = okc ? ldg_in<BF>(f2b, pc) : 0.f;
+                t[1][cc] = okc ? ldg_in<BF>(f2b, pc + dx) : 0.f;
+                t[2][cc] = okc ? ldg_in<BF>(f2b, pc + dy) : 0.f;
+                t[3][cc] = okc ? ldg_in<BF>(f2b, pc + dy + dx) : 0.f;
               }
 #pragma unroll
               for (int cc = 0; cc < CC; ++cc) {
@@ -1109,14 +1155,18 @@ template <bool FUSED>
 static int launch_corr(const char* fn, const float* f1, long long f1_bs, const float* f2, long long f2_bs,
                        const float* flow, long long flow_bs, float* out, long long out_bs, const GridArgs& g, int B,
                        int C, int H, int W, int shift, float slope, void* ws, size_t ws_bytes, cudaStream_t st,
-                       int pitch = 0) {
+                       int pitch = 0, int dt = 0, int pitch_in = 0) {
+  // dt = 1: f1 / f2 point to bf16 storage; f1_bs / f2_bs / pitch_in are in bf16 elements (pitch_in = 0: same as `pitch`)
   constexpr int CORR_SMEM = FUSED ? CORR_SMEM_FUSED : CORR_SMEM_PLAIN;
   static SmemAttrCache attr = {};
   if (int rc = ensure_dyn_smem(corr_kernel<FUSED>, CORR_SMEM, attr, fn)) return rc;
   // every H x W tensor of the call (f1, f2, flow, out) is stored with row pitch P >= W; P % 4 == 0 puts any width on the
   // TMA / vector paths (the tensor maps zero-fill columns >= W)
   const int P = pitch > 0 ? pitch : W;
-  if (P < W) return fail_arg(fn, "row pitch smaller than the width");
+  const int Pi = pitch_in > 0 ? pitch_in : P;
+  if (P < W || Pi < W) return fail_arg(fn, "row pitch smaller than the width");
+  if (dt != 0 && dt != 1) return fail_arg(fn, "dtype_in must be 0 (fp32) or 1 (bf16)");
+  if (dt == 0 && Pi != P) return fail_arg(fn, "fp32 inputs share the row pitch of flow / out");
   int vec_ok = (P % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec_ok && (P % 8 == 0) && (((long long)H * P) % 8 == 0) && (out_bs % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0))
     vec_ok = 2;  // every 8-pixel strip of every output plane is 32-byte aligned
@@ -1128,12 +1178,17 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
   if (nt > 0x7fffffffLL) return fail_arg(fn, "too many tiles");
   int ntiles = (int)nt;
   int grid = ntiles < sm_count() ? ntiles : sm_count();  // persistent: one CTA per SM
-  if (vec_in && !corr_no_tma()) {
+  if (dt == 1) vec_in = 1;   // bf16: the tensor maps check the alignment (pitch % 8, strides % 8, 16-byte bases)
+  if (vec_in && (dt == 1 || !corr_no_tma())) {
     constexpr int TSMEM = FUSED ? CORR_SMEM_TMA_FUSED : CORR_SMEM_TMA_PLAIN;
-    static SmemAttrCache tattr = {}, tattr_split = {}, tattr_pre = {}, tattr_pre_split = {};
+    static SmemAttrCache tattr = {}, tattr_split = {}, tattr_pre = {}, tattr_pre_split = {}, tattr_bf = {}, tattr_bf_split = {};
     CUtensorMap m1, m2;
-    if (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC, P) &&
-        make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC, P)) {
+    const bool maps_ok =
+        dt == 1 ? (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P16, TH, CC, Pi, 2) &&
+                   make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P16, FUSED ? FP_H : F2_H, CC, Pi, 2))
+                : (make_nchw_map(&m1, f1, f1_bs, B, C, H, W, F1_P, TH, CC, P) &&
+                   make_nchw_map(&m2, f2, f2_bs, B, C, H, W, FUSED ? FP_W : F2_P, FUSED ? FP_H : F2_H, CC, P));
+    if (maps_ok) {
       const int ctr = corr_ctr_on() ? 1 : 0;
       if (ctr) {
         static const unsigned long long zeros[32] = {0};
@@ -1145,7 +1200,7 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
       float4* tabW = nullptr;
       int* tabI = nullptr;
       // tap table from a pre-pass (fused launches): the table goes first in the workspace
-      if (FUSED && wsp != nullptr && (reinterpret_cast<uintptr_t>(wsp) & 255) == 0 && !corr_no_pretab() && !ctr && H < 32768 &&
+      if (FUSED && dt == 0 && wsp != nullptr && (reinterpret_cast<uintptr_t>(wsp) & 255) == 0 && !corr_no_pretab() && !ctr && H < 32768 &&
           W < 16384 && corr_tab_bytes(B, H, W) <= ws_left) {
         const size_t n = (size_t)B * H * W;
         tabW = reinterpret_cast<float4*>(wsp);
@@ -1167,19 +1222,22 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
         }
       }
       const int nthr = FUSED ? CORR_THREADS : T_PLAIN_THREADS;
-#define IRR_CORR_LAUNCH(SPLIT_, PRE_, CACHE_)                                                                              \
+#define IRR_CORR_LAUNCH(SPLIT_, PRE_, CACHE_, BF_)                                                                         \
   do {                                                                                                                     \
-    if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, SPLIT_, PRE_>, TSMEM, CACHE_, fn)) return rc;                       \
-    corr_tma_kernel<FUSED, SPLIT_, PRE_><<<grid, nthr, TSMEM, st>>>(m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, \
-                                                                   g, B, C, H, W, P, shift, slope, vec_ok, tiles_x,       \
-                                                                   tiles_y, ntiles, ctr, sp, tabW, tabI);                  \
+    if (int rc = ensure_dyn_smem(corr_tma_kernel<FUSED, SPLIT_, PRE_, BF_>, TSMEM, CACHE_, fn)) return rc;                  \
+    corr_tma_kernel<FUSED, SPLIT_, PRE_, BF_><<<grid, nthr, TSMEM, st>>>(m1, m2, f1, f1_bs, f2, f2_bs, flow, flow_bs, out,  \
+                                                                        out_bs, g, B, C, H, W, P, Pi, shift, slope, vec_ok, \
+                                                                        tiles_x, tiles_y, ntiles, ctr, sp, tabW, tabI);     \
   } while (0)
-      if (FUSED && tabW != nullptr) {
-        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, FUSED, tattr_pre_split);
-        else IRR_CORR_LAUNCH(false, FUSED, tattr_pre);
+      if (dt == 1) {
+        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, false, tattr_bf_split, true);
+        else IRR_CORR_LAUNCH(false, false, tattr_bf, true);
+      } else if (FUSED && tabW != nullptr) {
+        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, FUSED, tattr_pre_split, false);
+        else IRR_CORR_LAUNCH(false, FUSED, tattr_pre, false);
       } else {
-        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, false, tattr_split);
-        else IRR_CORR_LAUNCH(false, false, tattr);
+        if (sp.ksplit > 1) IRR_CORR_LAUNCH(true, false, tattr_split, false);
+        else IRR_CORR_LAUNCH(false, false, tattr, false);
       }
 #undef IRR_CORR_LAUNCH
       if (int rc = check_launch(fn)) return rc;
@@ -1191,6 +1249,11 @@ static int launch_corr(const char* fn, const float* f1, long long f1_bs, const f
       }
       return 0;
     }
+  }
+  if (dt == 1)
+  {
+    set_error("%s: bf16 inputs need 16-byte aligned rows (base %% 16 == 0, row pitch %% 8 == 0, batch stride %% 8 == 0)", fn);
+    return IRR_E_ALIGN;
   }
   corr_kernel<FUSED><<<grid, CORR_THREADS, CORR_SMEM, st>>>(f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H,
                                                             W, P, shift, slope, vec_ok, vec_in, tiles_x, tiles_y, ntiles);
@@ -1274,6 +1337,34 @@ int irr_warp_correlation_fwd_ws(const float* f1, long long f1_bs, const float* f
                                             f2_batch_shift, leaky_slope, workspace, workspace_bytes, as_stream(stream), pitch);
   return launch_corr<true>(fn, f1, f1_bs, f2, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
                            workspace, workspace_bytes, as_stream(stream), pitch);
+}
+
+int irr_warp_correlation_fwd_dt(const void* f1, long long f1_bs, const void* f2, long long f2_bs, int dtype_in, int in_pitch,
+                                const float* flow, long long flow_bs, const float* lin_x, const float* lin_y, float* out,
+                                long long out_bs, int B, int C, int H, int W, int H_im, int W_im, float div_flow, int max_disp,
+                                int f2_batch_shift, float leaky_slope, int grid_flags, void* workspace,
+                                size_t workspace_bytes, int pitch, irr_stream_t stream) {
+  const char* fn = "irr_warp_correlation_fwd_dt";
+  IRR_REQUIRE(f1 && f2 && out, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, fn, "non-positive size");
+  IRR_REQUIRE(max_disp == MD, fn, "only max_displacement = 4 (PWC parameters)");
+  IRR_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < B, fn, "f2_batch_shift out of range");
+  IRR_REQUIRE(dtype_in == IRR_DTYPE_F32 || dtype_in == IRR_DTYPE_BF16, fn, "dtype_in must be IRR_DTYPE_F32 or IRR_DTYPE_BF16");
+  if (dtype_in == IRR_DTYPE_F32)
+    return irr_warp_correlation_fwd_ws(static_cast<const float*>(f1), f1_bs, static_cast<const float*>(f2), f2_bs, flow, flow_bs,
+                                       lin_x, lin_y, out, out_bs, B, C, H, W, H_im, W_im, div_flow, max_disp, f2_batch_shift,
+                                       leaky_slope, grid_flags, workspace, workspace_bytes, pitch, stream);
+  const float* a = static_cast<const float*>(f1);   // the bf16 kernels reinterpret the pointers
+  const float* b = static_cast<const float*>(f2);
+  if (flow == nullptr) {
+    GridArgs g = make_grid_args(nullptr, nullptr, H, W, H, W, 1.f, 0);
+    return launch_corr<false>(fn, a, f1_bs, b, f2_bs, nullptr, 0, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
+                              workspace, workspace_bytes, as_stream(stream), pitch, 1, in_pitch);
+  }
+  IRR_REQUIRE(H_im > 0 && W_im > 0, fn, "non-positive image size");
+  GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
+  return launch_corr<true>(fn, a, f1_bs, b, f2_bs, flow, flow_bs, out, out_bs, g, B, C, H, W, f2_batch_shift, leaky_slope,
+                           workspace, workspace_bytes, as_stream(stream), pitch, 1, in_pitch);
 }
 
 int irr_warp_correlation_fwd(const float* f1, long long f1_bs, const float* f2, long long f2_bs, const float* flow,

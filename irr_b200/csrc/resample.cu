@@ -65,6 +65,26 @@ __global__ void round_bf16_kernel(const float* __restrict__ x, long long x_bs, f
   y[(size_t)b * y_bs + e] = __uint_as_float(r << 16);
 }
 
+// The same rounding with a second destination: packed bf16 STORAGE (2 bytes per element, its own batch stride / row pitch)
+// for the consumers that can read it (the correlation kernels, dtype_in = IRR_DTYPE_BF16).  y (fp32 layout) is optional.
+__global__ void round_bf16_store_kernel(const float* __restrict__ x, long long x_bs, int PX, float* __restrict__ y,
+                                        long long y_bs, unsigned short* __restrict__ y16, long long y16_bs, int P16, int C,
+                                        int H, int W, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int w = (int)(i % W);
+  long long r = i / W;
+  const int h = (int)(r % H);
+  r /= H;
+  const int c = (int)(r % C);
+  const long long b = r / C;
+  const size_t e = ((size_t)c * H + h) * PX + w;
+  const uint32_t u = __float_as_uint(__ldg(x + (size_t)b * x_bs + e));
+  const uint32_t q = ((u & 0x7fffffffu) > 0x7f800000u) ? ((u >> 16) | 0x0040u) : ((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+  if (y != nullptr) y[(size_t)b * y_bs + e] = __uint_as_float(q << 16);
+  y16[(size_t)b * y16_bs + ((size_t)c * H + h) * P16 + w] = (unsigned short)q;
+}
+
 // upsample_factor2 (models/irr_modules.py:21-27).
 __global__ void upsample_nearest2x_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ y,
                                           long long y_bs, int C, int H, int W, int OH, int OW, int PI, int PO, int exact,
@@ -280,6 +300,19 @@ int irr_round_bf16_fwd(const float* x, long long x_bs, float* y, long long y_bs,
   IRR_REQUIRE(B > 0 && C > 0 && HW > 0, fn, "non-positive size");
   long long total = (long long)B * C * HW;
   round_bf16_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(x, x_bs, y, y_bs, (long long)C * HW, total);
+  return check_launch(fn);
+}
+
+int irr_round_bf16_store_fwd(const float* x, long long x_bs, int x_pitch, float* y, long long y_bs, void* y16,
+                             long long y16_bs, int y16_pitch, int B, int C, int H, int W, irr_stream_t stream) {
+  const char* fn = "irr_round_bf16_store_fwd";
+  IRR_REQUIRE(x && y16, fn, "null pointer");
+  IRR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, fn, "non-positive size");
+  const int PX = x_pitch > 0 ? x_pitch : W, P16 = y16_pitch > 0 ? y16_pitch : W;
+  IRR_REQUIRE(PX >= W && P16 >= W, fn, "row pitch smaller than the width");
+  long long total = (long long)B * C * H * W;
+  round_bf16_store_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+      x, x_bs, PX, y, y_bs, static_cast<unsigned short*>(y16), y16_bs, P16, C, H, W, total);
   return check_launch(fn);
 }
 

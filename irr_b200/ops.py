@@ -60,12 +60,12 @@ def _launch(what: str, meta, fn, *args) -> None:
     _lib.check(rc, what)
 
 
-def _vp(t: torch.Tensor, name: str = "tensor") -> Tuple[int, int, int]:
+def _vp(t: torch.Tensor, name: str = "tensor", dtype=torch.float32) -> Tuple[int, int, int]:
     """(data_ptr, batch_stride, row_pitch) in elements of an NCHW channel-slice view whose rows may be stored with a
     pitch P >= W (``buf[:, a:b, :, :W]`` of a ``(B, C, H, P)`` buffer: stride(2) = P, stride(1) = H*P) — include/irr_b200.h,
     "ROW PITCH"."""
-    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
-        raise RuntimeError(f"irr_b200: {name} must be a 4-D fp32 CUDA tensor (got {t.dtype}, {t.device}, dim {t.dim()})")
+    if not (t.is_cuda and t.dtype == dtype and t.dim() == 4):
+        raise RuntimeError(f"irr_b200: {name} must be a 4-D {dtype} CUDA tensor (got {t.dtype}, {t.device}, dim {t.dim()})")
     B, Cc, H, W = t.shape
     s = t.stride()
     # a single row of a single channel has no pitch: 0 = "any" (callers merge it with the other operands' pitch)
@@ -95,6 +95,8 @@ def _pitch(name: str, *ps: int) -> int:
 
 def _is_pitched(t: torch.Tensor) -> Optional[bool]:
     """True / False: ``t`` has padded / dense rows; None: it has no pitch (one row of one channel) -> module default."""
+    if t.dtype != torch.float32:
+        return None
     P = _vp(t)[2]
     return (P != t.shape[3]) if P else None
 
@@ -208,9 +210,15 @@ def correlation(f1, f2, out=None, shift: int = 0, slope: float = 1.0, max_disp: 
     if out is None:
         out = _new(f1, D, H, W, pitched=_is_pitched(f1))
     assert out.shape == (B, D, H, W)
+    ws, nws = _corr_workspace(B, C, H, W, f1.device)
+    if f1.dtype == torch.bfloat16:   # bf16 STORAGE for f1 / f2 (include/irr_b200.h irr_warp_correlation_fwd_dt)
+        p1, s1, q1 = _vp(f1, "f1", torch.bfloat16); p2, s2, q2 = _vp(f2, "f2", torch.bfloat16); po, so, qo = _vp(out, "out")
+        _launch("correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_dt, p1, s1, p2, s2, DTYPE_BF16,
+                _pitch("correlation", q1, q2), None, 0, None, None, po, so, B, C, H, W, H, W, 1.0, max_disp, shift, slope, 0,
+                ws.data_ptr() if ws is not None else None, nws, qo, _stream())
+        return out
     p1, s1, q1 = _vp(f1, "f1"); p2, s2, q2 = _vp(f2, "f2"); po, so, qo = _vp(out, "out")
     P = _pitch("correlation", q1, q2, qo)
-    ws, nws = _corr_workspace(B, C, H, W, f1.device)
     _launch("correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, None, 0, None, None,
             po, so, B, C, H, W, H, W, 1.0, max_disp, shift, slope, 0, ws.data_ptr() if ws is not None else None, nws, P,
             _stream())
@@ -226,9 +234,17 @@ def warp_correlation(f1, f2, flow, height_im: int, width_im: int, div_flow: floa
         out = _new(f1, D, H, W, pitched=_is_pitched(f1))
     lx = host_linspace(W, f1.device) if lin_x is None else lin_x
     ly = host_linspace(H, f1.device) if lin_y is None else lin_y
+    ws, nws = _corr_workspace(B, C, H, W, f1.device, fused=True)
+    if f1.dtype == torch.bfloat16:
+        p1, s1, q1 = _vp(f1, "f1", torch.bfloat16); p2, s2, q2 = _vp(f2, "f2", torch.bfloat16)
+        pf, sf, qf = _vp(flow, "flow"); po, so, qo = _vp(out, "out")
+        _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_dt, p1, s1, p2, s2, DTYPE_BF16,
+                _pitch("warp_correlation", q1, q2), pf, sf, _p(lx, "lin_x", flow, W), _p(ly, "lin_y", flow, H), po, so, B, C, H, W,
+                height_im, width_im, div_flow, max_disp, shift, slope, _grid_mode, ws.data_ptr() if ws is not None else None,
+                nws, _pitch("warp_correlation", qf, qo), _stream())
+        return out
     p1, s1, q1 = _vp(f1, "f1"); p2, s2, q2 = _vp(f2, "f2"); pf, sf, qf = _vp(flow, "flow"); po, so, qo = _vp(out, "out")
     P = _pitch("warp_correlation", q1, q2, qf, qo)
-    ws, nws = _corr_workspace(B, C, H, W, f1.device, fused=True)
     _launch("warp_correlation", (B, C, H, W), _lib.load().irr_warp_correlation_fwd_ws, p1, s1, p2, s2, pf, sf,
             _p(lx, "lin_x", f1, W), _p(ly, "lin_y", f1, H), po, so, B, C, H, W, height_im, width_im, div_flow, max_disp,
             shift, slope, _grid_mode, ws.data_ptr() if ws is not None else None, nws, P, _stream())
@@ -417,6 +433,29 @@ def scale_channels(x, out=None, s_even: float = 1.0, s_odd: float = 1.0):
     _launch("scale_channels", None, _lib.load().irr_scale_channels_fwd, px, sx, po, so, B, C, H * (qx or qo or W), s_even, s_odd,
             _stream())
     return out
+
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+
+
+def empty_bf16(B: int, C: int, H: int, W: int, device) -> torch.Tensor:
+    """A (B, C, H, W) bf16 tensor whose rows are padded to a multiple of 8 elements (16 bytes): what the bf16 correlation
+    path needs (irr_warp_correlation_fwd_dt)."""
+    P = (W + 7) // 8 * 8
+    t = torch.empty((B, C, H, P), dtype=torch.bfloat16, device=device)
+    return t if P == W else t[:, :, :, :W]
+
+
+def round_bf16_store(x, round_in_place: bool = True, out16=None):
+    """Packed bf16 copy of ``x`` (round to nearest even) for the correlation's bf16 input path; with ``round_in_place`` ``x``
+    itself is also replaced by float(bf16(x)), as round_bf16(x, out=x) does — one pass over x for both."""
+    B, C, H, W = x.shape
+    if out16 is None:
+        out16 = empty_bf16(B, C, H, W, x.device)
+    px, sx, qx = _vp(x, "x"); p16, s16, q16 = _vp(out16, "out16", torch.bfloat16)
+    _launch("round_bf16_store", None, _lib.load().irr_round_bf16_store_fwd, px, sx, qx, px if round_in_place else None, sx, p16,
+            s16, q16, B, C, H, W, _stream())
+    return out16
 
 
 def round_bf16(x, out=None):

@@ -229,3 +229,65 @@ def test_mixed_pitch_is_refused(cuda):
     f = torch.from_numpy(rs(196, (1, 8, 9, 13)))
     with pytest.raises(RuntimeError):
         ops.correlation(pit(f, cuda), f.to(cuda))
+
+
+# ------------------------------------------------------------------ bf16 STORAGE of the correlation inputs
+@pytest.mark.parametrize("shape", [(2, 32, 47, 156), (1, 96, 24, 78), (2, 64, 24, 39), (16, 196, 6, 21), (2, 128, 12, 40),
+                                   (3, 17, 9, 13), (2, 32, 109, 256)])
+def test_correlation_bf16_storage(cuda, shape):
+    """irr_warp_correlation_fwd_dt with dtype_in = bf16 (BASELINE configs[4] "mixed bf16 features"; SURVEY.md §8(b) sketch):
+    f1 / f2 are read as packed bf16 (half the bytes), the arithmetic is the fp32 kernel's on the converted values — so the
+    result must equal, BIT FOR BIT, the fp32-storage kernel run on the same bf16-rounded values; and both match the oracle.
+    Plain, fused (warp) and the channel-split launches; odd widths (row pitch 8 for bf16, 4 for fp32)."""
+    from irr_b200 import ops
+    B, C, H, W = shape
+    him, wim = 16 * H, 16 * W
+    f = torch.from_numpy(rs(201, shape))
+    flow = torch.from_numpy(rs(203, (B, 2, H, W))) * torch.tensor([wim / W, him / H]).view(1, 2, 1, 1) * 0.05 * 2.5
+    if B == 3:   # one tile with wildly divergent flow: the footprint window does not fit, taps come from global memory
+        flow[0] = flow[0] * 20.0
+    sh = B // 2
+    fr = f.bfloat16().float()                       # the values both paths see
+    x = pit(f, cuda)                                # fp32 layout, rounded in place by the store op
+    x16 = ops.round_bf16_store(x, round_in_place=True)
+    assert x16.dtype == torch.bfloat16 and x16.stride(2) % 8 == 0
+    assert torch.equal(x.cpu(), fr) and torch.equal(x16.cpu().float(), fr)
+    pf = pit(flow, cuda)
+    a32 = nanbuf(B, 81, H, W, cuda); a16 = nanbuf(B, 81, H, W, cuda)
+    ops.correlation(x, x, out=a32, shift=sh, slope=0.1)
+    ops.correlation(x16, x16, out=a16, shift=sh, slope=0.1)
+    assert torch.isfinite(a16).all() and torch.equal(a16, a32)
+    w32 = nanbuf(B, 81, H, W, cuda); w16 = nanbuf(B, 81, H, W, cuda)
+    ops.warp_correlation(x, x, pf, him, wim, 0.05, out=w32, shift=sh, slope=0.1)
+    ops.warp_correlation(x16, x16, pf, him, wim, 0.05, out=w16, shift=sh, slope=0.1)
+    assert torch.isfinite(w16).all() and torch.equal(w16, w32)
+    if B * C * H * W <= 2_000_000:
+        ref = torch.nn.functional.leaky_relu(O.cost_volume(fr, torch.roll(fr, -sh, 0)), 0.1)
+        refw = torch.nn.functional.leaky_relu(O.cost_volume(fr, O.warp(torch.roll(fr, -sh, 0), flow, him, wim, 0.05)), 0.1)
+        assert (a16.cpu() - ref).abs().max().item() <= 1e-4 and (w16.cpu() - refw).abs().max().item() <= 1e-4
+
+
+def test_correlation_bf16_needs_aligned_rows(cuda):
+    """No unaligned bf16 path: a dense bf16 tensor with an odd width is refused (IRR_E_ALIGN), not mis-read."""
+    from irr_b200 import ops
+    x = torch.randn(1, 8, 9, 13, device=cuda).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.correlation(x, x)
+
+
+def test_irr_pwc_bf16_storage_is_output_identical(cuda):
+    """IRR_PWC with bf16-valued features: cost volumes fed from the packed bf16 copy == fed from the fp32 layout."""
+    import irr_b200
+    from irr_b200 import pwc_modules, ops
+    pwc_modules.set_conv_math(ops.MATH_TC_3XF16)
+    p = O.synthetic_params("IRR_PWC", seed=1234, gain=0.7)
+    m = irr_b200.IRR_PWC(None)
+    irr_b200.load_state_dict_strict(m, p)
+    m = m.to(cuda).eval().set_feature_dtype("bf16")
+    i1, i2, _ = O.synthetic_pair(1, 94, 156, seed=9, max_flow=5.0)
+    inp = {"input1": i1.to(cuda), "input2": i2.to(cuda)}
+    m.bf16_storage = True
+    a = m(inp)
+    m.bf16_storage = False
+    b = m(inp)
+    assert torch.equal(a["flow"], b["flow"]) and torch.equal(a["occ"], b["occ"])

@@ -61,7 +61,10 @@ def refmodels():
 
 def _state(ckpt):
     import irr_b200
-    sd = torch.load(os.path.join(CK, ckpt, "checkpoint_best.ckpt"), map_location="cpu", weights_only=True)["state_dict"]
+    path = os.path.join(CK, ckpt, "checkpoint_best.ckpt")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not staged (python scripts/stage_ref.py)")
+    sd = torch.load(path, map_location="cpu", weights_only=True)["state_dict"]
     return irr_b200.checkpoint.strip_prefix(sd)
 
 
