@@ -678,7 +678,8 @@ def main():
     pk = peaks()
     pairs = G * args.steps
     value = pairs / (ms * 1e-3)
-    s_in = 4
+    # bytes per f1 / f2 element the cost volumes read: 2 when the model feeds them from packed bf16 storage (config 5)
+    s_in = 2 if (cfg["feat"] == "bf16" and getattr(model, "bf16_storage", False)) else 4
     # dominant correlation launch = the finest-level call (largest algorithmic bytes)
     corr = [(k, v) for k, v in agg.items() if k[0] in ("correlation", "warp_correlation")]
     levels = []
@@ -759,7 +760,8 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "per_gpu_batch": B, "global_batch": G,
                    "parallelism": f"batch-sharded replicas x{world} (no data-path collective)",
-                   "conv_math": math_name, "features": cfg["feat"], "cuda_graph": graph is not None,
+                   "conv_math": math_name, "features": cfg["feat"] + (" (values in the fp32 layout for convs / warps; packed bf16 storage for the cost volumes' f1 / f2)"
+                                             if s_in == 2 else ""), "cuda_graph": graph is not None,
                    "l2": "per-step working set (GBs of level-4 activations) exceeds the 126 MB L2; no explicit flush",
                    "weights": weights_note},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * h1.numel() * 4,

@@ -291,3 +291,20 @@ def test_irr_pwc_bf16_storage_is_output_identical(cuda):
     m.bf16_storage = False
     b = m(inp)
     assert torch.equal(a["flow"], b["flow"]) and torch.equal(a["occ"], b["occ"])
+
+
+def test_round_bf16_store_special_values(cuda):
+    """irr_round_bf16_store_fwd == x.bfloat16() bit for bit (RNE, ties, subnormals, inf, NaN quieted), packed copy and the
+    optional in-place fp32 rounding; without round_in_place the source stays untouched."""
+    from irr_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 5, 7, 9, generator=g) * torch.logspace(-42, 30, 2 * 5 * 7 * 9).view(2, 5, 7, 9)
+    x.view(-1)[:8] = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), 1.00390625, 1.01171875, 3.3895314e38, 1e-45])
+    want = x.bfloat16()
+    src = pit(x, cuda)
+    y16 = ops.round_bf16_store(src, round_in_place=False)
+    assert torch.equal(y16.cpu().view(torch.int16), want.view(torch.int16)) and torch.equal(src.cpu(), x)
+    y16b = ops.round_bf16_store(src, round_in_place=True)
+    assert torch.equal(y16b.cpu().view(torch.int16), want.view(torch.int16)) and torch.equal(src.cpu(), want.float())
+    n16 = ops.round_bf16_store(torch.full((1, 1, 2, 8), float("nan"), device=cuda))
+    assert torch.isnan(n16.float()).all()
