@@ -140,6 +140,10 @@ int irr_correlation_generic_out_shape(int H, int W, int pad_size, int kernel_siz
 size_t irr_conv2d_packed_bytes(int Cout, int Cin, int ksize, int math);
 /* 1 if `math` can run this layer shape, 0 otherwise (the CUDA-core mode runs every k in {1,3} shape). */
 int irr_conv2d_math_supported(int Cout, int Cin, int ksize, int stride, int dilation, int math);
+/* 1 when IRR_MATH_FP32_SIMT runs this layer on the DIRECT thin-layer kernel (K = Cin*k*k <= 32, Cout <= 16: the first
+ * pyramid layer 3 -> 16 and the 16 -> 3 1x1 convs — pure HBM streams, one thread per output pixel, fp32 FMAs); that
+ * kernel honours row pitches, and the host side routes these layers to it whatever the default math mode is. */
+int irr_conv2d_direct_supported(int Cout, int Cin, int ksize);
 int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int Cin, int ksize, int math,
                             irr_stream_t stream);
 int irr_conv2d_fwd(const float* x, long long x_bs, const void* w_packed, const float* bias, const float* addend,

@@ -49,6 +49,7 @@ PROTOTYPES = {
                                           C.POINTER(c_i)],
     "irr_conv2d_packed_bytes": [c_i, c_i, c_i, c_i],
     "irr_conv2d_math_supported": [c_i, c_i, c_i, c_i, c_i, c_i],
+    "irr_conv2d_direct_supported": [c_i, c_i, c_i],
     "irr_conv2d_pack_weights": [c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp],
     "irr_conv2d_fwd": [c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_fp, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                        c_f, c_i, c_i, c_i, c_fp],

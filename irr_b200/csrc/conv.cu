@@ -5,9 +5,10 @@
 namespace irr {
 size_t simt_packed_bytes(int Cout, int Cin, int ks);
 int simt_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t st);
+bool simt_direct_supported(int Cout, int Cin, int ks);
 int simt_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
               float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil,
-              float slope, float alpha, cudaStream_t st);
+              float slope, float alpha, cudaStream_t st, int pitch_in, int pitch_out);
 size_t tc_packed_bytes(int Cout, int Cin, int ks, int math);
 int tc_pack(const float* w, void* out, int Cout, int Cin, int ks, int math, cudaStream_t st);
 int tc_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
@@ -48,6 +49,8 @@ int irr_conv2d_math_supported(int Cout, int Cin, int ksize, int stride, int dila
   return 0;
 }
 
+int irr_conv2d_direct_supported(int Cout, int Cin, int ksize) { return simt_direct_supported(Cout, Cin, ksize) ? 1 : 0; }
+
 int irr_conv2d_pack_weights(const float* w_oihw, void* w_packed, int Cout, int Cin, int ksize, int math,
                             irr_stream_t stream) {
   const char* fn = "irr_conv2d_pack_weights";
@@ -87,7 +90,8 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
   const char* fn = "irr_conv2d_fwd";
   const bool pitched = (x_pitch > 0 && x_pitch != W) ||
                        (y_pitch > 0 && y_pitch != (W + 2 * (((ksize - 1) * dilation) / 2) - dilation * (ksize - 1) - 1) / stride + 1);
-  IRR_REQUIRE(!pitched || math == IRR_MATH_TC_3XF16, fn, "row pitches are implemented by the IRR_MATH_TC_3XF16 path only");
+  IRR_REQUIRE(!pitched || math == IRR_MATH_TC_3XF16 || (math == IRR_MATH_FP32_SIMT && simt_direct_supported(Cout, Cin, ksize)), fn,
+              "row pitches are implemented by the IRR_MATH_TC_3XF16 path and the direct thin-layer kernel only");
   IRR_REQUIRE(x && w_packed && bias && y, fn, "null pointer");
   IRR_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, fn, "non-positive size");
   IRR_REQUIRE(ksize == 1 || ksize == 3, fn, "kernel_size must be 1 or 3");
@@ -95,7 +99,7 @@ int irr_conv2d_fwd_ws(const float* x, long long x_bs, const void* w_packed, cons
   IRR_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, fn, "w_packed must be 16-byte aligned");
   if (math == IRR_MATH_FP32_SIMT)
     return simt_conv(x, x_bs, w_packed, bias, addend, addend_bs, y, y_bs, B, Cin, H, W, Cout, ksize, stride, dilation,
-                     leaky_slope, alpha, as_stream(stream));
+                     leaky_slope, alpha, as_stream(stream), x_pitch, y_pitch);
   if (math == IRR_MATH_TC_3XTF32 || math == IRR_MATH_TC_TF32) {
     if (!tc_supported(Cout, Cin, ksize, stride, dilation)) {
       set_error("%s: layer shape not supported by the tcgen05 path (Cout=%d Cin=%d k=%d)", fn, Cout, Cin, ksize);

@@ -169,6 +169,71 @@ __global__ void pack_simt_kernel(const float* __restrict__ w, float* __restrict_
   out[i] = (n < Cout && k < K) ? __ldg(w + (size_t)n * K + k) : 0.f;
 }
 
+// ------------------------------------------------------------------------------------------------ direct kernel
+// Layers that are not a contraction worth a tile pipeline — K = Cin*k*k <= 32 and Cout <= 16: the first pyramid layer
+// 3 -> 16 (k 3, stride 2, pwc_modules.py:95-104) and the 16 -> 3 1x1 convs of the occlusion up-sampler's inputs
+// (IRR_PWC.py:44-45) — are pure HBM streams: one thread per output pixel, all K taps loaded first (K independent loads in
+// flight), weights broadcast from shared memory, every output channel of the pixel in registers, plane-coalesced stores.
+// fp32 FMAs in the reference's k order (c, ky, kx).  On the tensor-core kernel's gather variant these layers ran 4-10x
+// above their HBM time (3 -> 16 at 436 x 1024: 356 us against 31 us of bytes).  Row pitches are honoured (ABI 2).
+struct DirectArgs {
+  ConvArgs c;
+  int Pi, Po;
+};
+template <int K, int KS, int NP>
+__global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs q) {
+  constexpr int T = KS * KS;
+  const ConvArgs& p = q.c;
+  __shared__ __align__(16) float ws[K * NP];
+  __shared__ float bs[NP];
+  for (int i = threadIdx.x; i < K * NP; i += 256) ws[i] = __ldg(p.w + (i / NP) * p.N_pad + (i % NP));   // packed [K_pad][N_pad]
+  if (threadIdx.x < NP) bs[threadIdx.x] = threadIdx.x < p.Cout ? __ldg(p.bias + threadIdx.x) : 0.f;
+  __syncthreads();
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= p.Ho * p.Wo) return;
+  const int b = blockIdx.y;
+  const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+  const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+  const float* xb = p.x + (size_t)b * p.x_bs;
+  const size_t HWi = (size_t)p.H * q.Pi;
+  float v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int c = k / T, t = k - c * T, ky = t / KS, kx = t - ky * KS;
+    const int iy = iy0 + ky * p.dil, ix = ix0 + kx * p.dil;
+    const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+    v[k] = ok ? __ldg(xb + (size_t)c * HWi + (size_t)iy * q.Pi + ix) : 0.f;
+  }
+  float acc[NP];
+#pragma unroll
+  for (int n = 0; n < NP; ++n) acc[n] = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int n4 = 0; n4 < NP / 4; ++n4) {
+      const float4 w = *reinterpret_cast<const float4*>(&ws[k * NP + n4 * 4]);
+      acc[n4 * 4] = fmaf(v[k], w.x, acc[n4 * 4]);
+      acc[n4 * 4 + 1] = fmaf(v[k], w.y, acc[n4 * 4 + 1]);
+      acc[n4 * 4 + 2] = fmaf(v[k], w.z, acc[n4 * 4 + 2]);
+      acc[n4 * 4 + 3] = fmaf(v[k], w.w, acc[n4 * 4 + 3]);
+    }
+  }
+  const size_t HWo = (size_t)p.Ho * q.Po;
+  const size_t o = (size_t)oy * q.Po + ox;
+#pragma unroll
+  for (int n = 0; n < NP; ++n) {
+    if (n < p.Cout) {
+      float r = leaky(acc[n] + bs[n], p.slope) * p.alpha;
+      if (p.addend) r += __ldg(p.addend + (size_t)b * p.a_bs + (size_t)n * HWo + o);
+      p.y[(size_t)b * p.y_bs + (size_t)n * HWo + o] = r;
+    }
+  }
+}
+
+bool simt_direct_supported(int Cout, int Cin, int ks) {
+  return Cout <= 16 && ((ks == 3 && Cin == 3) || (ks == 1 && Cin == 16));
+}
+
 template <int KS>
 static void launch_simt(const ConvArgs& a, cudaStream_t st) {
   unsigned gm = (unsigned)((a.M + BM - 1) / BM);
@@ -200,7 +265,7 @@ int simt_pack(const float* w, void* out, int Cout, int Cin, int ks, cudaStream_t
 
 int simt_conv(const float* x, long long x_bs, const void* w, const float* bias, const float* addend, long long a_bs,
               float* y, long long y_bs, int B, int Cin, int H, int W, int Cout, int ks, int stride, int dil,
-              float slope, float alpha, cudaStream_t st) {
+              float slope, float alpha, cudaStream_t st, int pitch_in, int pitch_out) {
   ConvArgs a;
   a.x = x; a.x_bs = x_bs; a.w = (const float*)w; a.bias = bias; a.addend = addend; a.a_bs = a_bs; a.y = y; a.y_bs = y_bs;
   a.B = B; a.Cin = Cin; a.H = H; a.W = W; a.Cout = Cout; a.stride = stride; a.dil = dil;
@@ -211,6 +276,19 @@ int simt_conv(const float* x, long long x_bs, const void* w, const float* bias, 
   a.N_pad = round_up(Cout, 16);
   a.M = (long long)B * a.Ho * a.Wo;
   a.slope = slope; a.alpha = alpha;
+  const int Pi = pitch_in > 0 ? pitch_in : W, Po = pitch_out > 0 ? pitch_out : a.Wo;
+  if (Pi < W || Po < a.Wo) return fail_arg("irr_conv2d_fwd", "row pitch smaller than the width");
+  if (simt_direct_supported(Cout, Cin, ks) && B <= 65535) {
+    DirectArgs d;
+    d.c = a; d.Pi = Pi; d.Po = Po;
+    dim3 g((unsigned)((a.Ho * a.Wo + 255) / 256), (unsigned)B);
+    if (ks == 3) conv_direct_kernel<27, 3, 16><<<g, 256, 0, st>>>(d);
+    else if (Cout <= 4) conv_direct_kernel<16, 1, 4><<<g, 256, 0, st>>>(d);
+    else conv_direct_kernel<16, 1, 16><<<g, 256, 0, st>>>(d);
+    return check_launch("irr_conv2d_fwd");
+  }
+  if (Pi != W || Po != a.Wo)
+    return fail_arg("irr_conv2d_fwd", "row pitches are implemented by the IRR_MATH_TC_3XF16 path and the direct thin-layer kernel only");
   if (ks == 1) launch_simt<1>(a, st); else launch_simt<3>(a, st);
   return check_launch("irr_conv2d_fwd");
 }

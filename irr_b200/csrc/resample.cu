@@ -50,6 +50,20 @@ __global__ void scale_channels_kernel(const float* __restrict__ x, long long x_b
   y[(size_t)b * y_bs + (size_t)c * HW + pix] = __fmul_rn(v, (c & 1) ? s_odd : s_even);
 }
 
+__global__ void scale_channels_v4_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ y,
+                                         long long y_bs, int C, long long HW4, float s_even, float s_odd, long long total4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  long long q = i % HW4;
+  long long r = i / HW4;
+  int c = (int)(r % C);
+  int b = (int)(r / C);
+  float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * x_bs + (size_t)c * HW4 * 4) + q);
+  const float s = (c & 1) ? s_odd : s_even;
+  v.x = __fmul_rn(v.x, s); v.y = __fmul_rn(v.y, s); v.z = __fmul_rn(v.z, s); v.w = __fmul_rn(v.w, s);
+  reinterpret_cast<float4*>(y + (size_t)b * y_bs + (size_t)c * HW4 * 4)[q] = v;
+}
+
 // BASELINE config 5 ("mixed bf16 features"): y = float(bf16_rn(x)) — the feature pyramid carries bf16 VALUES (what a
 // `.bfloat16()` cast before the warp / correlation produces) in the fp32 NCHW layout every consumer already reads.
 __global__ void round_bf16_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ y, long long y_bs,
@@ -288,6 +302,12 @@ int irr_scale_channels_fwd(const float* x, long long x_bs, float* y, long long y
   IRR_REQUIRE(x && y, fn, "null pointer");
   IRR_REQUIRE(B > 0 && C > 0 && HW > 0, fn, "non-positive size");
   long long total = (long long)B * C * HW;
+  // 16-byte path: the concat-slice copies of the level loop (113 channels at 109 x 256 ...) are pure streams
+  if ((HW % 4) == 0 && (x_bs % 4) == 0 && (y_bs % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    scale_channels_v4_kernel<<<blocks_for(total / 4, 256), 256, 0, as_stream(stream)>>>(x, x_bs, y, y_bs, C, HW / 4, scale_even,
+                                                                                         scale_odd, total / 4);
+    return check_launch(fn);
+  }
   scale_channels_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(x, x_bs, y, y_bs, C, HW, scale_even,
                                                                                 scale_odd, total);
   return check_launch(fn);

@@ -7,8 +7,9 @@
 
 namespace irr {
 
-constexpr int WARP_CG = 8;  // channels per thread
-
+// WARP_CG channels per thread: 8 for feature maps; 4 for the 2- / 3-channel flow and image warps, whose throughput comes
+// from occupancy rather than from loads in flight per thread (measured: 8-wide at C = 3 was 30 % slower than the old loop).
+template <int WARP_CG>
 __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ x, long long x_bs,
                                                    const float* __restrict__ flow, long long flow_bs,
                                                    const float* __restrict__ minuend, long long m_bs,
@@ -31,12 +32,39 @@ __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ x, 
   if (bs >= B) bs -= B;
   const float* xp = x + (size_t)bs * x_bs;
   if (mask_out && c0 == 0) mask_out[(size_t)b * H * W + pix] = t.mask;   // the mask output is dense
-  int cend = min(c0 + WARP_CG, C);
-  for (int c = c0; c < cend; ++c) {
-    float val = 0.f;
-    if (t.mask != 0.f) val = gather_bilinear(xp + (size_t)c * HW, t, W, H, P);  // x_warp * mask (pwc_modules.py:133)
-    if (minuend) val = __fsub_rn(__ldg(minuend + (size_t)b * m_bs + (size_t)c * HW + pp), val);
-    out[(size_t)b * o_bs + (size_t)c * HW + pp] = val;
+  // All tap loads of the thread's channel group first (up to 32 + 8 independent loads in flight), then the arithmetic in
+  // grid_sampler's tap order, then the stores: a sequential channel loop left one channel's four loads outstanding per
+  // thread and the kernel at ~1.4 TB/s on the 436 x 1024 image warps.
+  const int nc = min(WARP_CG, C - c0);
+  const bool live = t.mask != 0.f;
+  const int x0 = min(max(t.x0, 0), W - 1), x1 = min(max(t.x0 + 1, 0), W - 1);
+  const int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
+  const size_t o00 = (size_t)y0 * P + x0, o01 = (size_t)y0 * P + x1, o10 = (size_t)y1 * P + x0, o11 = (size_t)y1 * P + x1;
+  const float* xc = xp + (size_t)c0 * HW;
+  float tp[WARP_CG][4], mn[WARP_CG];
+#pragma unroll
+  for (int j = 0; j < WARP_CG; ++j) {
+    const bool ok = live && j < nc;
+    const float* pc = xc + (size_t)j * HW;
+    tp[j][0] = ok ? __ldg(pc + o00) : 0.f;
+    tp[j][1] = ok ? __ldg(pc + o01) : 0.f;
+    tp[j][2] = ok ? __ldg(pc + o10) : 0.f;
+    tp[j][3] = ok ? __ldg(pc + o11) : 0.f;
+    mn[j] = (minuend && j < nc) ? __ldg(minuend + (size_t)b * m_bs + (size_t)(c0 + j) * HW + pp) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < WARP_CG; ++j) {
+    if (j < nc) {
+      float val = 0.f;
+      if (live) {   // same tap order and roundings as gather_bilinear / grid_sampler_2d_kernel; x_warp * mask (pwc_modules.py:133)
+        val = __fmul_rn(tp[j][0], t.w00);
+        val = fmaf(tp[j][1], t.w01, val);
+        val = fmaf(tp[j][2], t.w10, val);
+        val = fmaf(tp[j][3], t.w11, val);
+      }
+      if (minuend) val = __fsub_rn(mn[j], val);
+      out[(size_t)b * o_bs + (size_t)(c0 + j) * HW + pp] = val;
+    }
   }
 }
 
@@ -135,8 +163,10 @@ extern "C" int irr_warp_fwd(const float* x, long long x_bs, const float* flow, l
   IRR_REQUIRE(x_batch_shift >= 0 && x_batch_shift < B, fn, "x_batch_shift out of range");
   IRR_REQUIRE(B <= 65535, fn, "batch too large");
   GridArgs g = make_grid_args(lin_x, lin_y, H, W, H_im, W_im, div_flow, grid_flags);
-  dim3 grid((H * W + 255) / 256, (C + WARP_CG - 1) / WARP_CG, B);
-  warp_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_bs, flow, flow_bs, minuend, minuend_bs, out, out_bs, mask_out,
+  const int cg = C <= 4 ? 4 : 8;
+  dim3 grid((H * W + 255) / 256, (C + cg - 1) / cg, B);
+  auto kern = C <= 4 ? warp_kernel<4> : warp_kernel<8>;
+  kern<<<grid, 256, 0, as_stream(stream)>>>(x, x_bs, flow, flow_bs, minuend, minuend_bs, out, out_bs, mask_out,
                                                    g, B, C, H, W, P, x_batch_shift);
   return check_launch(fn);
 }

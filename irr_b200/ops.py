@@ -309,6 +309,11 @@ def conv_out_hw(H: int, W: int, ks: int, stride: int, dil: int) -> Tuple[int, in
     return (H + 2 * pad - dil * (ks - 1) - 1) // stride + 1, (W + 2 * pad - dil * (ks - 1) - 1) // stride + 1
 
 
+def direct_supported(Cout, Cin, ks) -> bool:
+    """The layer runs on the direct thin-layer kernel of the fp32 path (include/irr_b200.h irr_conv2d_direct_supported)."""
+    return bool(_lib.load().irr_conv2d_direct_supported(Cout, Cin, ks))
+
+
 def tc_supported(Cout, Cin, ks, stride, dil, math: int = MATH_TC_3XTF32) -> bool:
     return bool(_lib.load().irr_conv2d_math_supported(Cout, Cin, ks, stride, dil, math))
 
@@ -344,8 +349,9 @@ def conv2d(x, packed, bias, Cout: int, ks: int, stride: int = 1, dil: int = 1, s
            addend=None, alpha: float = 1.0, math: int = MATH_FP32_SIMT):
     B, Cin, H, W = x.shape
     Ho, Wo = conv_out_hw(H, W, ks, stride, dil)
-    if out is None:   # only the 3xF16 path understands pitched rows
-        out = _new(x, Cout, Ho, Wo, pitched=(_pitch_enabled and math == MATH_TC_3XF16))
+    if out is None:   # only the 3xF16 path and the direct thin-layer kernel understand pitched rows
+        out = _new(x, Cout, Ho, Wo, pitched=(_pitch_enabled and (math == MATH_TC_3XF16 or
+                                                                 (math == MATH_FP32_SIMT and direct_supported(Cout, Cin, ks)))))
     assert out.shape == (B, Cout, Ho, Wo), (out.shape, (B, Cout, Ho, Wo))
     px, sx, qx = _vp(x, "x"); po, so, qo = _vp(out, "out")
     pa, sa, qa = (_vp(addend, "addend") if addend is not None else (None, 0, qo))

@@ -45,6 +45,8 @@ class ConvBlock(nn.Sequential):
 
     def _math(self):
         m = _default_math
+        if m == ops.MATH_TC_3XF16 and ops.direct_supported(self.cout, self.cin, self.ks):
+            return ops.MATH_FP32_SIMT   # thin HBM-bound layers (3 -> 16, 16 -> 3 1x1): the direct fp32 kernel, not a tile pipeline
         if m != ops.MATH_FP32_SIMT and not ops.tc_supported(self.cout, self.cin, self.ks, self.stride, self.dil, m):
             m = ops.MATH_FP32_SIMT
         return m

@@ -308,3 +308,42 @@ def test_round_bf16_store_special_values(cuda):
     assert torch.equal(y16b.cpu().view(torch.int16), want.view(torch.int16)) and torch.equal(src.cpu(), want.float())
     n16 = ops.round_bf16_store(torch.full((1, 1, 2, 8), float("nan"), device=cuda))
     assert torch.isnan(n16.float()).all()
+
+
+# ------------------------------------------------------------------ direct thin-layer conv kernel (fp32 path)
+@pytest.mark.parametrize("case", [(2, 3, 45, 621, 16, 3, 2), (1, 3, 64, 96, 16, 3, 2), (2, 3, 33, 50, 9, 3, 1),
+                                  (2, 16, 47, 311, 3, 1, 1), (1, 16, 20, 64, 3, 1, 1)])
+def test_conv2d_direct_thin_layers(cuda, case):
+    """3 -> 16 (k 3, stride 2: first pyramid layer, pwc_modules.py:95-104) and 16 -> 3 1x1 (IRR_PWC.py:44-45) on the direct
+    kernel of the fp32 path: fp32 FMAs, dense and row-pitched operands (NaN pad columns), residual epilogue; and the module
+    wrapper routes these layers there in the default 3xF16 mode."""
+    from irr_b200 import ops, pwc_modules
+    B, Cin, H, W, Cout, k, s = case
+    assert ops.direct_supported(Cout, Cin, k)
+    torch.manual_seed(211)
+    x = torch.randn(B, Cin, H, W)
+    w = torch.from_numpy(rs(212, (Cout, Cin, k, k))) * float(np.sqrt(2.0 / (Cin * k * k)))
+    b = torch.from_numpy(rs(213, (Cout,))) * 0.1
+    Ho, Wo = ops.conv_out_hw(H, W, k, s, 1)
+    add = torch.from_numpy(rs(214, (B, Cout, Ho, Wo)))
+    ref = add.double() + 0.5 * torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s, padding=(k - 1) // 2), 0.1)
+    packed = ops.pack_weights(w.to(cuda), ops.MATH_FP32_SIMT)
+    out = nanbuf(B, Cout + 3, Ho, Wo, cuda)
+    ops.conv2d(pit(x, cuda), packed, b.to(cuda), Cout, k, s, 1, slope=0.1, out=out[:, 1:1 + Cout], addend=pit(add, cuda),
+               alpha=0.5, math=ops.MATH_FP32_SIMT)
+    got = out[:, 1:1 + Cout].cpu().double()
+    assert torch.isfinite(got).all() and (got - ref).abs().max().item() <= 1e-5
+    assert torch.isnan(out[:, :1]).all() and torch.isnan(out[:, 1 + Cout:]).all()
+    dense = ops.conv2d(x.to(cuda), packed, b.to(cuda), Cout, k, s, 1, slope=0.1, out=torch.empty(B, Cout, Ho, Wo, device=cuda),
+                       addend=add.to(cuda), alpha=0.5, math=ops.MATH_FP32_SIMT)
+    assert torch.equal(dense.cpu().double(), got)
+    pwc_modules.set_conv_math(ops.MATH_TC_3XF16)
+    blk = pwc_modules.conv(Cin, Cout, kernel_size=k, stride=s).to(cuda)
+    assert blk._math() == ops.MATH_FP32_SIMT
+    with torch.no_grad():
+        blk[0].weight.copy_(w.to(cuda)); blk[0].bias.copy_(b.to(cuda))
+        y = blk(x.to(cuda))
+    refy = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s, padding=(k - 1) // 2), 0.1)
+    assert (y.cpu().double() - refy).abs().max().item() <= 1e-5
