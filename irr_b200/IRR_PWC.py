@@ -240,7 +240,9 @@ class PWCNet(nn.Module):
         x1_raw = input_dict['input1']
         x2_raw = input_dict['input2']
         B, _, height_im, width_im = x1_raw.shape
-        with torch.no_grad():
+        # the kernels launch on the CURRENT device / stream: make the input's device current, as the reference's
+        # correlation.py:21 does (a model on cuda:1 must work while cuda:0 is current)
+        with torch.cuda.device_of(x1_raw), torch.no_grad():
             imgs = ops.stack_pair(x1_raw, x2_raw)  # (2B, 3, H, W), rows pitched when W % 4 != 0
             pyramid = self.feature_pyramid_extractor(imgs)
             pyr16 = [None] * (len(pyramid) + 1)

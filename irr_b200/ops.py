@@ -66,6 +66,9 @@ def _vp(t: torch.Tensor, name: str = "tensor", dtype=torch.float32) -> Tuple[int
     "ROW PITCH"."""
     if not (t.is_cuda and t.dtype == dtype and t.dim() == 4):
         raise RuntimeError(f"irr_b200: {name} must be a 4-D {dtype} CUDA tensor (got {t.dtype}, {t.device}, dim {t.dim()})")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"irr_b200: {name} lives on {t.device} but cuda:{torch.cuda.current_device()} is the current device — "
+                           f"wrap the call in `with torch.cuda.device_of(tensor):` (the kernels launch on the current device)")
     B, Cc, H, W = t.shape
     s = t.stride()
     # a single row of a single channel has no pitch: 0 = "any" (callers merge it with the other operands' pitch)
