@@ -52,7 +52,10 @@ def par():
         torch.cuda.current_stream().wait_stream(st)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / K
-ref = [o.clone() for o in (outs[0]["flow"], outs[1]["flow"])]
+for g in graphs:
+    g.replay()
+torch.cuda.synchronize()
+ref = [o.clone() for o in (outs[0]["flow"], outs[1]["flow"])]   # outputs of one replay each (capture does not execute)
 for name, fn in (("sequential", seq), ("two in flight", par), ("sequential", seq), ("two in flight", par)):
     fn()
     t = fn()
